@@ -1,0 +1,542 @@
+// bf16 tensor-core GEMM for sm_100a:  D[M,N] = A[M,K] * B[N,K]^T  (both operands K-major, fp32 accumulate)
+//
+//   TMA (cp.async.bulk.tensor, SWIZZLE_128B) -> 4-6 stage smem ring -> tcgen05.mma (M=128, N=BN, K=16)
+//   -> double-buffered fp32 accumulators in TMEM -> tcgen05.ld -> fused epilogue.
+//
+// One persistent CTA per SM, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner),
+// warps 2..5 = epilogue (one TMEM lane quadrant each; thread <-> output row).
+//
+// Two users share the pipeline:
+//   * MODE_GEMM  -- the encoder linears of the prompted CLIP towers and their dgrads
+//                   (reference: nn.MultiheadAttention in_proj/out_proj + mlp.c_fc/c_proj,
+//                   retrieval/models/clip/model.py:168-196) with bias / QuickGELU / residual /
+//                   dQuickGELU fused into the epilogue;
+//   * MODE_TOPK  -- the retrieval scorer (reference: `image_feats @ text_feats.t()` then a full
+//                   np.argsort per row, retrieval/methods/sprompt.py:509,559-567,597-599): the score
+//                   tile never leaves TMEM/registers; each epilogue thread keeps the running top-k
+//                   of its query row ordered by (score desc, gallery index asc).
+#include "ptx.cuh"
+#include "lpi_internal.h"
+
+namespace lpi {
+
+constexpr int BM = 128;
+constexpr int BK = 64;                 // 64 bf16 = 128 B = one SWIZZLE_128B row
+constexpr int UMMA_K = 16;
+constexpr int A_STAGE_BYTES = BM * BK * 2;
+constexpr int GEMM_THREADS = 192;
+constexpr int TOPK_MAX = 16;
+
+enum { MODE_GEMM = 0, MODE_TOPK = 1 };
+
+struct GemmArgs {
+    int M, N, K;
+    int epi;
+    const float* bias;             // [N] fp32 or null
+    const float* resid;            // [M, ldo] fp32 (EPI_RESID) -- may alias out_f32
+    float* out_f32;                // [M, ldo]
+    __nv_bfloat16* out_bf16;       // [M, ldo]
+    __nv_bfloat16* out2_bf16;      // [M, ldo] second output (pre-activation) or null
+    const __nv_bfloat16* aux_bf16; // [M, ldo] (EPI_DGELU: saved pre-activation)
+    int ldo;
+    // MODE_TOPK
+    int k;                         // top-k (<= TOPK_MAX)
+    int n_chunks;                  // gallery split per query tile (load balance)
+    int tiles_per_chunk;
+    long long gallery_offset;      // global index of gallery row 0 of this shard
+    float* topk_scores;            // [n_chunks, M, k]
+    int* topk_idx;                 // [n_chunks, M, k]
+};
+
+template <int BN>
+struct Cfg {
+    static constexpr int B_STAGE_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+    static constexpr int STAGES = (BN == 256) ? 4 : 6;
+    static constexpr int TMEM_COLS = 2 * BN;
+    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+    static constexpr int LIST_OFF = BAR_OFF + 256;
+    static constexpr int SMEM_BYTES = LIST_OFF + BM * TOPK_MAX * 8 + 1024;   // +1024 alignment slack
+};
+
+// The sequence of (m0, n0) tiles a CTA walks is a pure function of blockIdx, so each warp role
+// re-derives it independently -- no inter-warp broadcast of scheduling decisions.
+template <int MODE, int BN>
+struct TileWalk {
+    int num_m, num_n;
+    // GEMM
+    int tile, total;
+    // TOPK
+    int item, n_items, n_cur, n_end, q_tile, chunk;
+    int tiles_per_chunk;
+    __device__ TileWalk(const GemmArgs& p) {
+        num_m = (p.M + BM - 1) / BM;
+        num_n = (p.N + BN - 1) / BN;
+        if (MODE == MODE_GEMM) {
+            tile = blockIdx.x;
+            total = num_m * num_n;
+        } else {
+            tiles_per_chunk = p.tiles_per_chunk;
+            n_items = num_m * p.n_chunks;
+            item = blockIdx.x;
+            begin_item();
+        }
+    }
+    __device__ void begin_item() {
+        if (item < n_items) {
+            q_tile = item % num_m;          // chunk-major: concurrent CTAs stream the same gallery region (L2 reuse)
+            chunk = item / num_m;
+            n_cur = chunk * tiles_per_chunk;
+            n_end = min(num_n, n_cur + tiles_per_chunk);
+        }
+    }
+    // returns false when the CTA is out of work; `first`/`last` flag the ends of a top-k work item
+    __device__ bool next(int& m0, int& n0, bool& first, bool& last) {
+        if (MODE == MODE_GEMM) {
+            if (tile >= total) return false;
+            m0 = (tile % num_m) * BM;       // M fastest: neighbouring CTAs share the weight (B) tile
+            n0 = (tile / num_m) * BN;
+            first = last = true;
+            tile += gridDim.x;
+            return true;
+        } else {
+            while (item < n_items && n_cur >= n_end) {   // empty chunk (cannot happen with sane args) or item done
+                item += gridDim.x;
+                begin_item();
+            }
+            if (item >= n_items) return false;
+            m0 = q_tile * BM;
+            n0 = n_cur * BN;
+            first = (n_cur == chunk * tiles_per_chunk);
+            ++n_cur;
+            last = (n_cur >= n_end);
+            if (last) {
+                item += gridDim.x;
+                begin_item();
+            }
+            return true;
+        }
+    }
+};
+
+__device__ __forceinline__ float quick_gelu(float z) { return z / (1.0f + __expf(-1.702f * z)); }
+__device__ __forceinline__ float quick_gelu_grad(float z) {
+    float s = 1.0f / (1.0f + __expf(-1.702f * z));
+    return s * (1.0f + 1.702f * z * (1.0f - s));
+}
+
+// 32 accumulator columns of one output row -> global memory, with the fused epilogue op.
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, const uint32_t (&r)[32], int row, int col0) {
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    if (EPI != EPI_F32 && EPI != EPI_ACC_F32 && EPI != EPI_DGELU_BF16 && EPI != EPI_BF16) {
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float4 b = __ldg(b4 + j);
+            v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+        }
+    }
+    if (row >= p.M) return;
+    const size_t off = size_t(row) * p.ldo + col0;
+    if (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_ACC_F32) {
+        const float4* s4 = reinterpret_cast<const float4*>((EPI == EPI_ACC_F32 ? p.out_f32 : p.resid) + off);
+        float4* d4 = reinterpret_cast<float4*>(p.out_f32 + off);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float4 s = s4[j];
+            v[4 * j] += s.x; v[4 * j + 1] += s.y; v[4 * j + 2] += s.z; v[4 * j + 3] += s.w;
+            d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        if (p.out_bf16) {   // optional bf16 shadow of the fp32 stream (A operand of the next dgrad GEMM)
+            uint4* o4 = reinterpret_cast<uint4*>(p.out_bf16 + off);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                o4[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                   pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+        }
+        return;
+    }
+    if (EPI == EPI_F32 || EPI == EPI_BIAS_F32) {
+        float4* d4 = reinterpret_cast<float4*>(p.out_f32 + off);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        return;
+    }
+    if (EPI == EPI_BIAS_GELU_BF16) {
+        if (p.out2_bf16) {   // keep the pre-activation for the backward pass
+            uint4* z4 = reinterpret_cast<uint4*>(p.out2_bf16 + off);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                z4[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                                   pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = quick_gelu(v[j]);
+    }
+    if (EPI == EPI_DGELU_BF16) {
+        const uint4* z4 = reinterpret_cast<const uint4*>(p.aux_bf16 + off);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint4 z = z4[j];
+            const __nv_bfloat162* zz = reinterpret_cast<const __nv_bfloat162*>(&z);
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                float2 f = __bfloat1622float2(zz[t]);
+                v[8 * j + 2 * t] *= quick_gelu_grad(f.x);
+                v[8 * j + 2 * t + 1] *= quick_gelu_grad(f.y);
+            }
+        }
+    }
+    uint4* o4 = reinterpret_cast<uint4*>(p.out_bf16 + off);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        o4[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                           pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+}
+
+template <int MODE, int BN, int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs p) {
+    using C = Cfg<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t bar_base = smem_base + C::BAR_OFF;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + 2 + a); };
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + C::BAR_OFF + 8 * (2 * C::STAGES + 4));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int num_k = p.K / BK;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < C::STAGES; ++s) {
+                mbar_init(full_bar(s), 1);
+                mbar_init(empty_bar(s), 1);
+            }
+            for (int a = 0; a < 2; ++a) {
+                mbar_init(tfull_bar(a), 1);
+                mbar_init(tempty_bar(a), 4);
+            }
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc<C::TMEM_COLS>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            TileWalk<MODE, BN> walk(p);
+            int stage = 0;
+            uint32_t phase = 0;
+            int m0, n0;
+            bool first, last;
+            while (walk.next(m0, n0, first, last)) {
+                for (int kb = 0; kb < num_k; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1);
+                    mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
+                    const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+                    tma_load_2d(sa, &tmA, full_bar(stage), kb * BK, m0);
+                    tma_load_2d(sa + A_STAGE_BYTES, &tmB, full_bar(stage), kb * BK, n0);
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer (single thread)
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc(kFmtBF16, BM, BN, 0, 0);
+            TileWalk<MODE, BN> walk(p);
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0;
+            int m0, n0;
+            bool first, last;
+            while (walk.next(m0, n0, first, last)) {
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < num_k; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+                    const uint64_t da = make_desc_kmajor_sw128(sa);
+                    const uint64_t db = make_desc_kmajor_sw128(sa + A_STAGE_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k)   // +32 B per K step inside the 128 B swizzle row
+                        umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    umma_commit(empty_bar(stage));           // smem slot reusable once these MMAs retire
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(tfull_bar(acc));                 // accumulator complete -> epilogue
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue warps (2..5)
+        const int quad = warp & 3;                 // TMEM lane quadrant this warp may touch
+        const int r_local = quad * 32 + lane;      // accumulator row owned by this thread
+        TileWalk<MODE, BN> walk(p);
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        int m0, n0;
+        bool first, last;
+        // MODE_TOPK running state: sorted list (desc score, asc index) in smem, column-major [j][row]
+        float* l_sc = reinterpret_cast<float*>(smem_gen + C::LIST_OFF);
+        int* l_id = reinterpret_cast<int*>(smem_gen + C::LIST_OFF + BM * TOPK_MAX * 4);
+        float thr = -INFINITY;
+        int cnt = 0;
+        while (walk.next(m0, n0, first, last)) {
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            const int row = m0 + r_local;
+            if (MODE == MODE_TOPK && first) { thr = -INFINITY; cnt = 0; }
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t r[32];
+                const uint32_t taddr = tmem_base + uint32_t(acc * BN + c * 32) + (uint32_t(quad * 32) << 16);
+                LPI_TMEM_LD_X32(taddr, r);
+                tmem_ld_wait();
+                if (MODE == MODE_GEMM) {
+                    epilogue_chunk<EPI>(p, r, row, n0 + c * 32);
+                } else {
+                    const int col0 = n0 + c * 32;
+                    if (col0 + 32 > p.N) {            // ragged gallery tail: rows past N were zero-filled by TMA
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (col0 + j >= p.N) r[j] = 0xff800000u;   // -inf
+                    }
+                    float m = __uint_as_float(r[0]);
+#pragma unroll
+                    for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(r[j]));
+                    if (m > thr) {                    // rare after warm-up: ~k*ln(N/k) insertions per row in total
+                        const int k = p.k;
+#pragma unroll 1
+                        for (int j = 0; j < 32; ++j) {
+                            const float v = __uint_as_float(r[j]);
+                            if (v > thr) {            // strict: an equal score with a larger index never displaces
+                                int pos = cnt < k ? cnt : k - 1;
+                                while (pos > 0 && l_sc[(pos - 1) * BM + r_local] < v) {
+                                    l_sc[pos * BM + r_local] = l_sc[(pos - 1) * BM + r_local];
+                                    l_id[pos * BM + r_local] = l_id[(pos - 1) * BM + r_local];
+                                    --pos;
+                                }
+                                l_sc[pos * BM + r_local] = v;
+                                l_id[pos * BM + r_local] = int(p.gallery_offset) + col0 + j;
+                                if (cnt < k) ++cnt;
+                                if (cnt == k) thr = l_sc[(k - 1) * BM + r_local];
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            if (MODE == MODE_TOPK && last) {
+                // item (q_tile, chunk) finished: m0 identifies q_tile; the chunk is n0's
+                const int chunk = (n0 / BN) / p.tiles_per_chunk;
+                if (row < p.M) {
+                    float* os = p.topk_scores + (size_t(chunk) * p.M + row) * p.k;
+                    int* oi = p.topk_idx + (size_t(chunk) * p.M + row) * p.k;
+                    for (int j = 0; j < p.k; ++j) {
+                        os[j] = j < cnt ? l_sc[j * BM + r_local] : -INFINITY;
+                        oi[j] = j < cnt ? l_id[j * BM + r_local] : 0x7fffffff;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc<C::TMEM_COLS>(tmem_base);
+    }
+}
+
+// ------------------------------------------------------------------------------------ host side
+static PFN_encodeTiled g_encode = nullptr;
+
+int ensure_tma_encoder() {
+    if (g_encode) return 0;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn)
+        return set_error(LPI_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable (%s)", cudaGetErrorString(e));
+    g_encode = reinterpret_cast<PFN_encodeTiled>(fn);
+    return 0;
+}
+
+// 2D row-major [rows, cols] tensor map with a [box_rows, box_cols] box, SWIZZLE_128B.
+int make_tmap_2d(CUtensorMap* m, const void* ptr, CUtensorMapDataType dt, int elem_bytes, uint64_t rows, uint64_t cols,
+                 uint64_t ld_elems, uint32_t box_rows, uint32_t box_cols) {
+    if (int rc = ensure_tma_encoder()) return rc;
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld_elems * elem_bytes) & 15))
+        return set_error(LPI_ERR_ARG, "TMA operand must be 16-byte aligned (ptr=%p ld=%llu)", ptr, (unsigned long long)ld_elems);
+    if (box_cols * elem_bytes != 128 || box_rows > 256)
+        return set_error(LPI_ERR_ARG, "bad TMA box %ux%u", box_rows, box_cols);
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {ld_elems * elem_bytes};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode(m, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(LPI_ERR_CUDA, "cuTensorMapEncodeTiled failed: %d", int(r));
+    return 0;
+}
+
+static int g_num_sms = 0;
+int num_sms() {
+    if (!g_num_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_num_sms <= 0) g_num_sms = 148;
+    }
+    return g_num_sms;
+}
+
+template <int MODE, int BN, int EPI>
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, int grid, cudaStream_t st) {
+    auto kern = gemm_tn_kernel<MODE, BN, EPI>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES);
+        if (e != cudaSuccess) return set_error(LPI_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        configured = true;
+    }
+    kern<<<grid, GEMM_THREADS, Cfg<BN>::SMEM_BYTES, st>>>(tmA, tmB, a);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_error(LPI_ERR_CUDA, "gemm launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+template <int BN>
+static int launch_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, int grid, cudaStream_t st) {
+    switch (a.epi) {
+        case EPI_BIAS_BF16: return launch<MODE_GEMM, BN, EPI_BIAS_BF16>(tmA, tmB, a, grid, st);
+        case EPI_BIAS_GELU_BF16: return launch<MODE_GEMM, BN, EPI_BIAS_GELU_BF16>(tmA, tmB, a, grid, st);
+        case EPI_BIAS_RESID_F32: return launch<MODE_GEMM, BN, EPI_BIAS_RESID_F32>(tmA, tmB, a, grid, st);
+        case EPI_F32: return launch<MODE_GEMM, BN, EPI_F32>(tmA, tmB, a, grid, st);
+        case EPI_BIAS_F32: return launch<MODE_GEMM, BN, EPI_BIAS_F32>(tmA, tmB, a, grid, st);
+        case EPI_ACC_F32: return launch<MODE_GEMM, BN, EPI_ACC_F32>(tmA, tmB, a, grid, st);
+        case EPI_DGELU_BF16: return launch<MODE_GEMM, BN, EPI_DGELU_BF16>(tmA, tmB, a, grid, st);
+        case EPI_BF16: return launch<MODE_GEMM, BN, EPI_BF16>(tmA, tmB, a, grid, st);
+    }
+    return set_error(LPI_ERR_ARG, "unknown epilogue %d", a.epi);
+}
+
+}  // namespace lpi
+
+using namespace lpi;
+
+extern "C" int lpi_gemm_bf16(const void* A, const void* B, int M, int N, int K, int epi, const void* bias,
+                             const void* resid, void* out, void* out2, const void* aux, int ldo, int tile_n, void* stream) {
+    if (M <= 0 || N <= 0 || K <= 0) return set_error(LPI_ERR_ARG, "gemm: empty problem %dx%dx%d", M, N, K);
+    if (K % BK) return set_error(LPI_ERR_ARG, "gemm: K=%d must be a multiple of %d", K, BK);
+    if (N % 128) return set_error(LPI_ERR_ARG, "gemm: N=%d must be a multiple of 128", N);
+    if (ldo < N || (ldo % 8)) return set_error(LPI_ERR_ARG, "gemm: bad ldo=%d", ldo);
+    const bool need_bias = (epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU_BF16 || epi == EPI_BIAS_RESID_F32 || epi == EPI_BIAS_F32);
+    if (need_bias && !bias) return set_error(LPI_ERR_ARG, "gemm: epilogue %d needs a bias", epi);
+    if (epi == EPI_BIAS_RESID_F32 && !resid) return set_error(LPI_ERR_ARG, "gemm: residual epilogue needs resid");
+    if (epi == EPI_DGELU_BF16 && !aux) return set_error(LPI_ERR_ARG, "gemm: dgelu epilogue needs the saved pre-activation");
+    if (!out) return set_error(LPI_ERR_ARG, "gemm: null output");
+    int bn = tile_n;
+    const int sms = num_sms();
+    if (bn == 0) {   // pick the tile width with the better wave efficiency
+        auto eff = [&](int b) {
+            if (N % b) return 0.0;
+            long tiles = long((M + BM - 1) / BM) * (N / b);
+            long waves = (tiles + sms - 1) / sms;
+            return double(tiles) / double(waves * sms);
+        };
+        bn = (eff(256) + 0.03 >= eff(128)) ? 256 : 128;   // prefer the wide tile unless quantisation hurts
+    }
+    if (bn != 128 && bn != 256) return set_error(LPI_ERR_ARG, "gemm: tile_n must be 0, 128 or 256");
+    if (N % bn) return set_error(LPI_ERR_ARG, "gemm: N=%d not a multiple of tile_n=%d", N, bn);
+    CUtensorMap tmA, tmB;
+    if (int rc = make_tmap_2d(&tmA, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, K, K, BM, BK)) return rc;
+    if (int rc = make_tmap_2d(&tmB, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, N, K, K, bn, BK)) return rc;
+    GemmArgs a{};
+    a.M = M; a.N = N; a.K = K; a.epi = epi; a.ldo = ldo;
+    a.bias = static_cast<const float*>(bias);
+    a.resid = static_cast<const float*>(resid);
+    a.aux_bf16 = static_cast<const __nv_bfloat16*>(aux);
+    a.out2_bf16 = static_cast<__nv_bfloat16*>(out2);
+    if (epi == EPI_BIAS_RESID_F32 || epi == EPI_F32 || epi == EPI_ACC_F32 || epi == EPI_BIAS_F32) {
+        a.out_f32 = static_cast<float*>(out);
+        a.out_bf16 = (epi == EPI_BIAS_RESID_F32 || epi == EPI_ACC_F32) ? static_cast<__nv_bfloat16*>(out2) : nullptr;
+        a.out2_bf16 = nullptr;
+    } else {
+        a.out_bf16 = static_cast<__nv_bfloat16*>(out);
+    }
+    const long tiles = long((M + BM - 1) / BM) * (N / bn);
+    const int grid = int(tiles < sms ? tiles : sms);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return bn == 256 ? launch_epi<256>(tmA, tmB, a, grid, st) : launch_epi<128>(tmA, tmB, a, grid, st);
+}
+
+extern "C" int lpi_sim_topk_chunks(int n_queries, int n_gallery, int* n_chunks_out) {
+    // Work items = query tiles x gallery chunks; pick the chunk count that fills whole waves of SMs.
+    const int sms = num_sms();
+    const int qt = (n_queries + BM - 1) / BM;
+    const int nt = (n_gallery + 255) / 256;
+    int best = 1;
+    double best_eff = 0;
+    for (int c = 1; c <= 64 && c <= nt; ++c) {
+        const int tpc = (nt + c - 1) / c;
+        if ((nt + tpc - 1) / tpc != c) continue;          // would leave an empty chunk
+        long items = long(qt) * c;
+        long waves = (items + sms - 1) / sms;
+        double eff = double(items) / double(waves * sms);
+        // each chunk restarts the top-k warm-up, so only accept more chunks for a real gain
+        if (eff > best_eff + 0.02) { best_eff = eff; best = c; }
+    }
+    *n_chunks_out = best;
+    return 0;
+}
+
+extern "C" int lpi_sim_topk_bf16(const void* Q, const void* G, int n_queries, int n_gallery, int dim, int k,
+                                 long long gallery_offset, int n_chunks, float* part_scores, int* part_idx, void* stream) {
+    if (n_queries <= 0 || n_gallery <= 0) return set_error(LPI_ERR_ARG, "sim_topk: empty problem");
+    if (dim % BK) return set_error(LPI_ERR_ARG, "sim_topk: dim=%d must be a multiple of %d", dim, BK);
+    if (k < 1 || k > TOPK_MAX) return set_error(LPI_ERR_ARG, "sim_topk: k=%d out of range [1,%d]", k, TOPK_MAX);
+    if (n_chunks < 1) return set_error(LPI_ERR_ARG, "sim_topk: n_chunks=%d", n_chunks);
+    if (gallery_offset + n_gallery > 0x7fffffffLL) return set_error(LPI_ERR_ARG, "sim_topk: gallery index exceeds int32");
+    const int nt = (n_gallery + 255) / 256;
+    if (n_chunks > nt) return set_error(LPI_ERR_ARG, "sim_topk: n_chunks=%d > gallery tiles=%d", n_chunks, nt);
+    CUtensorMap tmA, tmB;
+    if (int rc = make_tmap_2d(&tmA, Q, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, n_queries, dim, dim, BM, BK)) return rc;
+    if (int rc = make_tmap_2d(&tmB, G, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, n_gallery, dim, dim, 256, BK)) return rc;
+    GemmArgs a{};
+    a.M = n_queries; a.N = n_gallery; a.K = dim;
+    a.k = k; a.n_chunks = n_chunks;
+    a.tiles_per_chunk = (nt + n_chunks - 1) / n_chunks;
+    if (long(a.tiles_per_chunk) * (n_chunks - 1) >= nt)
+        return set_error(LPI_ERR_ARG, "sim_topk: n_chunks=%d leaves an empty chunk for %d tiles", n_chunks, nt);
+    a.gallery_offset = gallery_offset;
+    a.topk_scores = part_scores;
+    a.topk_idx = part_idx;
+    const long items = long((n_queries + BM - 1) / BM) * n_chunks;
+    const int sms = num_sms();
+    const int grid = int(items < sms ? items : sms);
+    return launch<MODE_TOPK, 256, EPI_F32>(tmA, tmB, a, grid, static_cast<cudaStream_t>(stream));
+}

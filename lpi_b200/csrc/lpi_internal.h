@@ -1,0 +1,22 @@
+// Internal declarations shared by the .cu translation units of liblpi_b200.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include "../../include/lpi_b200.h"
+
+namespace lpi {
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int set_error(int code, const char* fmt, ...);   // records lpi_last_error(), returns `code`
+int check_launch(const char* what);              // cudaGetLastError -> error code
+int num_sms();
+int ensure_tma_encoder();
+int make_tmap_2d(CUtensorMap* m, const void* ptr, CUtensorMapDataType dt, int elem_bytes, uint64_t rows, uint64_t cols,
+                 uint64_t ld_elems, uint32_t box_rows, uint32_t box_cols);
+
+}  // namespace lpi
