@@ -91,6 +91,13 @@ def topk_merge(part_scores: torch.Tensor, part_idx: torch.Tensor) -> Tuple[torch
     _chk(part_scores, torch.float32, "part_scores")
     _chk(part_idx, torch.int32, "part_idx")
     n_parts, nq, k = part_scores.shape
+    max_parts = max(2, 256 // k)          # the merge kernel holds <= 256 candidates per query
+    while n_parts > max_parts:            # hierarchical merge for very wide fan-in
+        groups = [topk_merge(part_scores[i:i + max_parts].contiguous(), part_idx[i:i + max_parts].contiguous())
+                  for i in range(0, n_parts, max_parts)]
+        part_scores = torch.stack([g[0] for g in groups])
+        part_idx = torch.stack([g[1] for g in groups])
+        n_parts = part_scores.shape[0]
     os_ = torch.empty(nq, k, device=part_scores.device, dtype=torch.float32)
     oi = torch.empty(nq, k, device=part_scores.device, dtype=torch.int32)
     call("topk_merge", ptr(part_scores), ptr(part_idx), n_parts, nq, k, ptr(os_), ptr(oi), stream_ptr())

@@ -143,3 +143,51 @@ def make_retrieval_set(n_img: int = 1000, caps_per_img: int = 5, dim: int = 512,
     cat_i = [i % n_tasks for i in range(n_img)]
     cat_t = [(t // caps_per_img) % n_tasks for t in range(n_img * caps_per_img)]
     return img, txt, img2txt, txt2img, cat_i, cat_t
+
+
+# ------------------------------------------------------------------------------------------------
+# Large-gallery sweep (BASELINE.json configs[4])
+# ------------------------------------------------------------------------------------------------
+GALLERY_BLOCK = 65536      # rows are generated in fixed blocks keyed on the block index, so any
+                           # sharding of the gallery sees bit-identical rows
+
+
+def gallery_gt(n_queries: int, n_gallery: int) -> torch.Tensor:
+    """Ground-truth gallery row of query q: (q * 199999) mod N (int64, host)."""
+    return (torch.arange(n_queries, dtype=torch.int64) * 199999) % n_gallery
+
+
+def _gallery_block(block: int, dim: int, seed: int, device) -> torch.Tensor:
+    g = torch.Generator(device=device).manual_seed(seed * 1000003 + 7 * block + 1)
+    x = torch.randn(GALLERY_BLOCK, dim, generator=g, device=device, dtype=torch.float32)
+    return x / x.norm(dim=-1, keepdim=True)
+
+
+def make_gallery_shard(n_gallery: int, lo: int, hi: int, n_queries: int, dim: int = 512, seed: int = 5,
+                       device="cuda", signal: float = 0.2):
+    """Rows [lo, hi) of the synthetic gallery as bf16 plus ALL queries (bf16, identical on every rank).
+
+    gallery row i = normalize(randn) (block-keyed generator); query q = normalize(signal * G[gt(q)] + noise/sqrt(dim)).
+    Every rank walks all blocks (cheap: the generator runs at HBM speed) and keeps its own slice, so no
+    communication is needed to build the workload.  Values depend on the device type of the generator
+    (CPU and CUDA Philox streams differ) but not on the sharding."""
+    device = torch.device(device)
+    gt = gallery_gt(n_queries, n_gallery).to(device)
+    shard = torch.empty(hi - lo, dim, device=device, dtype=torch.bfloat16)
+    q_src = torch.empty(n_queries, dim, device=device, dtype=torch.float32)
+    n_blocks = (n_gallery + GALLERY_BLOCK - 1) // GALLERY_BLOCK
+    for b in range(n_blocks):
+        b_lo, b_hi = b * GALLERY_BLOCK, min(n_gallery, (b + 1) * GALLERY_BLOCK)
+        x = _gallery_block(b, dim, seed, device)[: b_hi - b_lo]
+        s_lo, s_hi = max(lo, b_lo), min(hi, b_hi)
+        if s_lo < s_hi:
+            shard[s_lo - lo: s_hi - lo] = x[s_lo - b_lo: s_hi - b_lo].to(torch.bfloat16)
+        sel = ((gt >= b_lo) & (gt < b_hi)).nonzero().flatten()
+        if sel.numel():
+            # queries are built from the bf16-rounded gallery row, i.e. from what the scorer sees
+            q_src[sel] = x[gt[sel] - b_lo].to(torch.bfloat16).float()
+    g = torch.Generator(device=device).manual_seed(seed * 1000003 + 999331)
+    noise = torch.randn(n_queries, dim, generator=g, device=device, dtype=torch.float32) / math.sqrt(dim)
+    q = signal * q_src + noise
+    q = (q / q.norm(dim=-1, keepdim=True)).to(torch.bfloat16)
+    return shard, q, gt.cpu()

@@ -328,3 +328,46 @@ def train_step(sd: Dict[str, Tensor], factors: Dict[str, Tensor], images: Tensor
         "losses": {k: float(v.detach()) for k, v in losses.items()},
         "grads": {k: fac[k].grad.detach() for k in FACTOR_NAMES},
     }
+
+
+# ----------------------------------------------------------------------------------------
+# CPU baseline leg of bench.py: the reference's own ranking procedure, literally
+# (methods/sprompt.py:509 dense matmul, :559-567 / :597-599 argsort + np.where)
+# ----------------------------------------------------------------------------------------
+
+def reference_ranks_argsort(scores: np.ndarray, gt: Sequence[Sequence[int]]) -> np.ndarray:
+    """rank[i] = min over ground truths g of the position of g in np.argsort(row)[::-1]."""
+    ranks = np.zeros(scores.shape[0])
+    for index, score in enumerate(scores):
+        inds = np.argsort(score)[::-1]
+        rank = 1e20
+        for g in gt[index]:
+            tmp = np.where(inds == g)[0][0]
+            if tmp < rank:
+                rank = tmp
+        ranks[index] = rank
+    return ranks
+
+
+def dense_scores(queries: Tensor, gallery: Tensor) -> Tensor:
+    """`image_feats @ text_feats.t()` (sprompt.py:509) in fp32 on the host cores."""
+    return queries.float() @ gallery.float().t()
+
+
+def audit_topk(got_idx: np.ndarray, want_idx: np.ndarray, q_row: Tensor, gallery: Tensor, tol: float = 4e-7) -> str:
+    """Near-tie audit of one query's top-k list (SURVEY.md section 8(d) scorer parity protocol).
+    'exact' = identical lists; 'near' = every differing position swaps two items whose fp64 scores
+    differ by < tol (fp32 accumulation-order noise); 'bad' otherwise."""
+    if np.array_equal(got_idx, want_idx):
+        return "exact"
+    q64 = q_row.double()
+    for a, b in zip(got_idx.tolist(), want_idx.tolist()):
+        if a == b:
+            continue
+        if a < 0 or a >= gallery.shape[0]:
+            return "bad"
+        sa = float(q64 @ gallery[a].double())
+        sb = float(q64 @ gallery[b].double())
+        if abs(sa - sb) >= tol:
+            return "bad"
+    return "near"

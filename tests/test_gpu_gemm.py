@@ -1,0 +1,72 @@
+"""-m gpu checks of the tcgen05/TMA GEMM with its fused epilogues against an fp32 torch matmul of the same
+bf16 operands (floating-point kernel: tolerance = bf16 output rounding, written below)."""
+import pytest
+import torch
+
+from lpi_b200 import ops
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(M, N, K, epi, tile_n, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    a = torch.randn(M, K, generator=g).cuda().bfloat16()
+    w = (torch.randn(N, K, generator=g) * K ** -0.5).cuda().bfloat16()
+    bias = torch.randn(N, generator=g).cuda()
+    resid = torch.randn(M, N, generator=g).cuda()
+    aux = torch.randn(M, N, generator=g).cuda().bfloat16()
+    ref = a.float() @ w.float().t()
+    kw, second = {}, None
+    if epi == ops.EPI_BIAS_BF16:
+        want, kw = ref + bias, dict(bias=bias)
+    elif epi == ops.EPI_BIAS_GELU_BF16:
+        z = ref + bias
+        want = z * torch.sigmoid(1.702 * z)
+        kw = dict(bias=bias, out2=torch.empty(M, N, device="cuda", dtype=torch.bfloat16))
+        second = (kw["out2"], z)
+    elif epi == ops.EPI_BIAS_RESID_F32:
+        want = resid + ref + bias
+        kw = dict(bias=bias, resid=resid, out2=torch.empty(M, N, device="cuda", dtype=torch.bfloat16))
+        second = (kw["out2"], want)
+    elif epi == ops.EPI_F32:
+        want = ref
+    elif epi == ops.EPI_BIAS_F32:
+        want, kw = ref + bias, dict(bias=bias)
+    elif epi == ops.EPI_ACC_F32:
+        want, kw = resid + ref, dict(out=resid.clone())
+    elif epi == ops.EPI_DGELU_BF16:
+        zf = aux.float()
+        s = torch.sigmoid(1.702 * zf)
+        want, kw = ref * (s * (1 + 1.702 * zf * (1 - s))), dict(aux=aux)
+    else:
+        want = ref
+    out = ops.gemm(a, w, epi, tile_n=tile_n, **kw)
+    scale = max(1.0, want.abs().max().item())
+    tol = (2 ** -8 if out.dtype == torch.bfloat16 else 2e-5) * scale      # bf16 rounding / fp32 accumulation order
+    assert (out.float() - want).abs().max().item() <= tol
+    if second is not None:
+        assert (second[0].float() - second[1]).abs().max().item() <= 2 ** -8 * max(1.0, second[1].abs().max().item())
+
+
+@pytest.mark.parametrize("M,N,K", [(100, 128, 64), (300, 512, 512), (4928, 1536, 512), (13632, 2304, 768),
+                                   (13632, 768, 3072), (1, 128, 64)])
+@pytest.mark.parametrize("tile_n", [0, 128, 256])
+def test_gemm_shapes(M, N, K, tile_n):
+    if tile_n and N % tile_n:
+        pytest.skip("N not a multiple of the tile")
+    _case(M, N, K, ops.EPI_F32, tile_n)
+
+
+@pytest.mark.parametrize("epi", range(8))
+def test_gemm_epilogues(epi):
+    _case(1000, 768, 768, epi, 0)
+    _case(333, 512, 2048, epi, 128, seed=1)
+
+
+def test_gemm_rejects_bad_shapes():
+    from lpi_b200._lib import LpiError
+
+    a = torch.zeros(8, 60, device="cuda", dtype=torch.bfloat16)
+    w = torch.zeros(128, 60, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(LpiError):
+        ops.gemm(a, w, ops.EPI_F32)

@@ -1,0 +1,134 @@
+"""-m gpu parity tests of the retrieval scorer: CUDA path (through the C ABI) vs the oracle on the same
+seeded inputs.  Bar: top-k indices and Recall@K bit-exact (ties -> lowest index)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from lpi_b200 import ops, retrieval as R, synthetic as S
+from oracle import lpi_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _oracle_topk(q, g, k):
+    s = (q.float().cpu() @ g.float().cpu().t()).numpy()
+    return O.topk_lowest_index(s, k) + (s,)
+
+
+@pytest.mark.parametrize("nq,ng,dim,chunks", [(1, 1, 64, 1), (128, 256, 64, 1), (100, 1000, 512, 1), (300, 5000, 512, 3),
+                                              (1000, 20000, 512, 0), (257, 70001, 512, 0), (37, 9, 512, 1)])
+def test_sim_topk_matches_oracle(nq, ng, dim, chunks):
+    gen = torch.Generator().manual_seed(nq * 7 + ng)
+    q = torch.randn(nq, dim, generator=gen).bfloat16()
+    g = torch.randn(ng, dim, generator=gen).bfloat16()
+    if ng > 5:
+        g[5] = g[3]                         # exact ties: the lower index must win
+    k = 10
+    v, i = ops.sim_topk(q.cuda(), g.cuda(), k, 0, chunks)
+    wv, wi, s = _oracle_topk(q, g, k)
+    got_i = i.cpu().numpy()
+    kk = min(k, ng)
+    assert (got_i[:, kk:] == 0x7FFFFFFF).all()                 # ragged: missing entries are (-inf, INT_MAX)
+    bad = 0
+    for r in range(nq):
+        verdict = O.audit_topk(got_i[r, :kk], wi[r, :kk], q[r], g)
+        assert verdict != "bad", (r, got_i[r], wi[r])
+        bad += verdict == "near"
+    assert bad <= max(1, nq // 200)                             # accumulation-order near-ties are rare
+    assert np.allclose(v.cpu().numpy()[:, :kk], wv[:, :kk], rtol=0, atol=2e-5 * max(1.0, np.abs(wv[:, :kk]).max()))
+
+
+def test_gallery_offset_and_shard_merge_equals_unsharded():
+    gen = torch.Generator().manual_seed(3)
+    q = torch.randn(500, 512, generator=gen).bfloat16().cuda()
+    g = torch.randn(30000, 512, generator=gen).bfloat16().cuda()
+    v0, i0 = ops.sim_topk(q, g, 10)
+    for world in (2, 3, 8):
+        parts = []
+        for r in range(world):
+            lo, hi = R.shard_bounds(g.shape[0], world, r, align=256)
+            parts.append(ops.sim_topk(q, g[lo:hi], 10, lo))
+        v, i = ops.topk_merge(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]))
+        assert torch.equal(i, i0) and torch.equal(v, v0)        # score of a pair does not depend on the sharding
+
+
+def test_topk_rows_and_merge_ties():
+    gen = torch.Generator().manual_seed(11)
+    s = torch.randn(70, 4001, generator=gen)
+    s[:, 100] = s[:, 7]
+    s[:, 4000] = s[:, 0]
+    v, i = ops.topk_rows(s.cuda(), 10)
+    wv, wi = O.topk_lowest_index(s.numpy(), 10)
+    assert np.array_equal(i.cpu().numpy(), wi) and np.array_equal(v.cpu().numpy(), wv)
+    # wide fan-in merge (hierarchical above 25 parts)
+    ps = torch.randn(40, 33, 10, generator=gen).sort(dim=-1, descending=True)[0]
+    pi = torch.arange(40 * 33 * 10, dtype=torch.int32).view(40, 33, 10)
+    mv, mi = ops.topk_merge(ps.cuda(), pi.cuda())
+    flat_s = ps.permute(1, 0, 2).reshape(33, -1).numpy()
+    flat_i = pi.permute(1, 0, 2).reshape(33, -1).numpy()
+    order = np.lexsort((flat_i, -flat_s), axis=1)[:, :10]
+    assert np.array_equal(mi.cpu().numpy(), np.take_along_axis(flat_i, order, 1))
+
+
+@pytest.mark.parametrize("name", ["recall_flickr_seed2.pt", "recall_small_seed5.pt"])
+def test_recall_matches_reference_golden(name):
+    """Recall@K dict bit-exact against the fixture produced by the REAL reference's itm_eval."""
+    g = torch.load(os.path.join(GOLDEN, name), weights_only=False)
+    m = g["meta"]
+    img, txt, img2txt, txt2img, cat_i, cat_t = S.make_retrieval_set(m["n_img"], m["caps_per_img"], 512, m["n_tasks"],
+                                                                    seed=m["seed"], signal=m.get("signal", 0.15))
+    got = R.itm_eval_features(img.cuda(), txt.cuda(), txt2img, img2txt, cat_i, cat_t, m["n_tasks"], precision="fp32")
+    assert got == g["result"]
+    s = (img @ txt.t()).numpy()
+    got_dense = R.itm_eval(s, np.ascontiguousarray(s.T), txt2img, img2txt, cat_i, cat_t, m["n_tasks"])
+    assert got_dense == g["result"]
+
+
+def test_fp32_split_scores_match_fp32_dot():
+    gen = torch.Generator().manual_seed(21)
+    a = torch.randn(64, 512, generator=gen)
+    b = torch.randn(300, 512, generator=gen)
+    a, b = a / a.norm(dim=-1, keepdim=True), b / b.norm(dim=-1, keepdim=True)
+    v, i = R.search_topk(a.cuda(), b.cuda(), 10, precision="fp32")
+    s64 = (a.double() @ b.double().t())
+    wv, wi = torch.sort(s64, dim=1, descending=True, stable=True)
+    assert torch.equal(i.cpu().long(), wi[:, :10])
+    assert (v.cpu().double() - wv[:, :10]).abs().max() < 3e-7
+
+
+def test_l2_normalize_and_recall_counts_edge_cases():
+    x = torch.randn(33, 512).cuda()
+    y, n = ops.l2_normalize(x, want_norm=True)
+    assert torch.allclose(y, x / x.norm(dim=-1, keepdim=True), atol=1e-6)
+    top = torch.tensor([[3, 1, 2], [0, 0, 0], [9, 9, 9]], dtype=torch.int32).cuda()
+    ptr, idx = R.gt_csr([[2], [], [5, 9]])
+    counts, rank = ops.recall_counts(top, ptr.cuda(), idx.cuda(), torch.tensor([0, 1, 1], dtype=torch.int32).cuda(), 2,
+                                     want_rank=True)
+    assert rank.tolist() == [2, 3, 0]
+    assert counts.tolist() == [[0, 1, 1, 1], [1, 1, 1, 2]]
+
+
+def test_large_gallery_property_full_size_subsample():
+    """BASELINE-size property check: on a 1M-row gallery, sampled queries' top-10 equal the oracle's, and
+    sharding the gallery leaves every list unchanged."""
+    ng, nq = 1_000_000, 4096
+    shard, q, gt = S.make_gallery_shard(ng, 0, ng, nq, 512, device="cuda")
+    v, i = ops.sim_topk(q, shard, 10)
+    lo, hi = R.shard_bounds(ng, 2, 1, align=256)
+    a = ops.sim_topk(q, shard[:lo], 10, 0)
+    b = ops.sim_topk(q, shard[lo:], 10, lo)
+    v2, i2 = ops.topk_merge(torch.stack([a[0], b[0]]), torch.stack([a[1], b[1]]))
+    assert torch.equal(i, i2) and torch.equal(v, v2)
+    sub = torch.arange(0, nq, 128)
+    g_host = shard.cpu().float()
+    s = (q[sub].cpu().float() @ g_host.t()).numpy()
+    _, wi = O.topk_lowest_index(s, 10)
+    got = i[sub].cpu().numpy()
+    for r in range(len(sub)):
+        assert O.audit_topk(got[r], wi[r], q[sub[r]].cpu(), g_host) != "bad"
+    # the planted ground truth is found far more often than chance
+    hit10 = (i.cpu().long() == gt[:, None]).any(1).float().mean().item()
+    assert hit10 > 0.2
