@@ -468,7 +468,7 @@ extern "C" int lpi_gemm_bf16(const void* A, const void* B, int M, int N, int K, 
             long waves = (tiles + sms - 1) / sms;
             return double(tiles) / double(waves * sms);
         };
-        bn = (eff(256) + 0.03 >= eff(128)) ? 256 : 128;   // prefer the wide tile unless quantisation hurts
+        bn = (N % 256 == 0 && eff(256) + 0.03 >= eff(128)) ? 256 : 128;   // prefer the wide tile unless quantisation hurts
     }
     if (bn != 128 && bn != 256) return set_error(LPI_ERR_ARG, "gemm: tile_n must be 0, 128 or 256");
     if (N % bn) return set_error(LPI_ERR_ARG, "gemm: N=%d not a multiple of tile_n=%d", N, bn);
