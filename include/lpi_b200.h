@@ -83,6 +83,101 @@ int lpi_split_bf16(const float* x, int n, int dim, int n_terms, int role, void* 
 /* x[n,dim] fp32 -> x/||x||_2 (no epsilon, models/slinet.py:122,133); in place allowed. */
 int lpi_l2_normalize(const float* x, int n, int dim, float* out, float* norm_out /* [n] or NULL */, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Fused multi-head attention (flash-style; scores never leave registers).
+ * replaces: nn.MultiheadAttention inside ResidualAttentionBlock.attention, models/clip/model.py:172,183-185
+ *           (+ the causal mask built at model.py:347-353) and its autograd backward.
+ * qkv [B*L, 3*H*64] bf16 (row = b*L + l; columns q | k | v), out / d_out [B*L, H*64] bf16, lse2 [B*H*L] fp32
+ * (log2-domain log-sum-exp saved by the forward for the backward), delta_ws [B*H*L] fp32 scratch, dqkv like qkv.
+ * ------------------------------------------------------------------------------------------------ */
+int lpi_attn_fwd(const void* qkv, void* out, float* lse2, int B, int L, int H, int causal, void* stream);
+int lpi_attn_bwd(const void* qkv, const void* out, const void* d_out, const float* lse2, float* delta_ws, void* dqkv,
+                 int B, int L, int H, int causal, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * LayerNorm in fp32 (models/clip/model.py:154-160; eps inside the sqrt, biased variance).
+ * fwd: x [M,D] fp32 -> out_f32 and/or out_bf16 (either may be NULL).
+ * bwd: g = (accumulate ? g : 0) + dLN(dy; x, gamma); optional bf16 shadow of g (A operand of the next dgrad GEMM).
+ * D in {128, 256, 512, 768, 1024}.
+ * ------------------------------------------------------------------------------------------------ */
+int lpi_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* out_f32, void* out_bf16, long long M, int D,
+                      float eps, void* stream);
+int lpi_layernorm_bwd(const float* dy, const float* x, const float* gamma, float* g, void* g_bf16, long long M, int D, float eps,
+                      int accumulate, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Vision front end (VisionTransformer.forward, models/clip/model.py:227-250).
+ * im2col: images [B,3,R,R] fp32 -> patch rows [B*(R/P)^2, 3*P*P] bf16 in conv1.weight.view(D,-1) column order, so that
+ *         conv1 (kernel = stride = P, no bias) is one lpi_gemm_bf16.
+ * assemble: row 0 = class_embedding + pos[0]; rows 1..P = prompt_table[sel[b]] (NO positional term, model.py:240-248);
+ *           rows P+1.. = patch_emb + pos[1..]; then ln_pre.  P = 0 / prompt_table NULL = un-prompted CLIP (extract_vector).
+ *           prompt_table [n_tables, P, D] fp32, sel [B] int32 or NULL (= table 0 for every sample).
+ * assemble_bwd: d_prompt[t,p,:] = sum_{b: sel[b]=t} dLN(g[b,1+p,:]; prompt_table[t,p,:], ln_pre.weight)   (overwrites d_prompt)
+ * ------------------------------------------------------------------------------------------------ */
+int lpi_im2col_patches(const float* images, void* out_bf16, int B, int resolution, int patch, void* stream);
+int lpi_assemble_vision(const float* patch_emb, const float* cls, const float* pos, const float* prompt_table, const int* sel,
+                        const float* ln_gamma, const float* ln_beta, float* x_out, int B, int n_patch, int P, int D, float eps,
+                        void* stream);
+int lpi_assemble_vision_bwd(const float* g, const float* prompt_table, const int* sel, const float* ln_gamma, float* d_prompt,
+                            int B, int L, int P, int n_tables, int D, float eps, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Text front end (PromptLearner.forward splice + TextEncoder positional add,
+ * models/clip/prompt_learner.py:133-163, 52-53): x[b,l] = (1 <= l <= P ? ctx_table[sel[b]][l-1] : token_embedding[tok[b,l]]) + pos[l].
+ * ctx_table NULL = extract_vector path (raw "X" embeddings, prompt_learner.py:118-126).  tokens int64 [B,L].
+ * bwd: d_ctx[t,p,:] = sum_{b: sel[b]=t} g[b,1+p,:]   (overwrites d_ctx)
+ * ------------------------------------------------------------------------------------------------ */
+int lpi_assemble_text(const float* token_embedding, const long long* tokens, const float* pos, const float* ctx_table,
+                      const int* sel, float* x_out, int B, int L, int P, int D, void* stream);
+int lpi_assemble_text_bwd(const float* g, const int* sel, float* d_ctx, int B, int L, int P, int n_tables, int D, void* stream);
+/* Opt-in deep-prompt injection (the intended semantics of the dead branch at models/clip/model.py:190-193):
+ * x[b, 1+p, :] += prompt[sel[b], p, :] before block `layer`; its backward is lpi_assemble_text_bwd on the block-input gradient. */
+int lpi_inject_prompt_rows(float* x, const float* prompt, const int* sel, int B, int L, int P, int D, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Encoder heads: feat[b] = normalize(LN(x[row_idx[b]]) @ proj), proj [D,E] fp32 row-major
+ * (ln_post + proj, model.py:254-257; ln_final + EOT gather + text_projection, prompt_learner.py:57-61; L2 norm slinet.py:122,133).
+ * z_out [B,E] = un-normalised features (kept for the backward).
+ * bwd: g[row_idx[b], :] = d/dx given dfeat (gradient wrt the normalised feature) and/or dz_direct (gradient wrt the raw
+ *      projection z); either may be NULL.  Rows are ASSIGNED; the caller zeroes g first.
+ * ------------------------------------------------------------------------------------------------ */
+int lpi_head_fwd(const float* x, const int* row_idx, const float* ln_gamma, const float* ln_beta, const float* proj, float* z_out,
+                 float* feat_out, int B, int D, int E, float eps, void* stream);
+int lpi_head_bwd(const float* dfeat, const float* dz_direct, const float* z, const float* x, const int* row_idx, const float* ln_gamma,
+                 const float* proj, float* g, void* g_bf16, int B, int D, int E, float eps, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * DecomposedPrompt (models/prompts/prompts.py:38-57): Y[l,p,d] = mean_k dim1[l,k] dim2[p,k] dim3[d,k], dim1 shared by both
+ * modalities.  bwd consumes dense upstream gradients g_vis [L,P,Dv], g_txt [L,P,Dt]; ws = 2*L*P*r floats.
+ * ------------------------------------------------------------------------------------------------ */
+int lpi_prompt_fwd(const float* dim1_share, const float* dim2_vis, const float* dim2_txt, const float* dim3_vis, const float* dim3_txt,
+                   float* vis_out, float* txt_out, int L, int P, int Dv, int Dt, int r, void* stream);
+int lpi_prompt_bwd(const float* dim1_share, const float* dim2_vis, const float* dim2_txt, const float* dim3_vis, const float* dim3_txt,
+                   const float* g_vis, const float* g_txt, float* ws, float* d_dim1, float* d_dim2_vis, float* d_dim2_txt,
+                   float* d_dim3_vis, float* d_dim3_txt, int L, int P, int Dv, int Dt, int r, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Losses (models/slinet.py:137-183, loss/loss.py:6-33,75-87) and optimiser (methods/sprompt.py:253-254).
+ * sgemm: C[m,n] = alpha * sum_k A[m*a_m + k*a_k] * B[k*b_k + n*b_n] + beta * C  -- exact fp32 products for the B x B logits,
+ *        d logits -> d features, the 9 x 9 alignment logits.
+ * clip_loss_logits: loss = weight * 1/2 [CE(S, arange) + CE(S^T, arange)]; dlogits (optional) = d loss / d S.  lse_ws = 2n floats.
+ * task_loss: nt_bxent_loss over the rows of X [R, n] (flattened prompts of tasks 0..R-1, R <= 16) including the reference's
+ *        double sigmoid; loss_out (+)= weight * loss; grad_last_row [n] (+)= d/dX[R-1] (the only trainable row).
+ *        part_ws = n_part*R*R floats, coef_out = R floats.
+ * ------------------------------------------------------------------------------------------------ */
+int lpi_sgemm_f32(const float* A, const float* B, float* C, int M, int N, int K, long long a_m, long long a_k, long long b_k,
+                  long long b_n, long long ldc, float alpha, float beta, void* stream);
+int lpi_clip_loss_logits(const float* logits, int n, float weight, float* lse_ws, float* loss_out, float* dlogits, void* stream);
+int lpi_row_mean(const float* x, float* out, int rows, int D, float scale, void* stream);
+int lpi_add_rowconst(float* G, const float* v, long long rows, int D, float alpha, int accumulate, void* stream);
+int lpi_task_loss(const float* X, int R, long long n, const int* target, float temperature, float weight, float* part_ws, int n_part,
+                  float* loss_out, int loss_accumulate, float* coef_out, float* grad_last_row, int grad_accumulate, void* stream);
+int lpi_sgd_momentum_step(float* w, const float* g, float* v, long long n, float lr, float momentum, float weight_decay,
+                          int first_step, void* stream);
+/* sel[b] = argmin_t min_c sum_d |f[b,d] - centers[t,c,d]| (methods/sprompt.py:336-368); centers [T,C,E]; sel int64 [B]. */
+int lpi_nearest_center_l1(const float* feats, const float* centers, int B, int n_tasks, int n_centers, int E, long long* sel_out,
+                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif

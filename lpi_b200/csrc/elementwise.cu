@@ -1,0 +1,502 @@
+// Bandwidth-bound kernels of the prompted CLIP towers: LayerNorm fwd/bwd, patch extraction, token assembly
+// (CLS / prompt rows / patches, + positional embedding, + ln_pre), text embedding gather + prompt splice,
+// and the encoder heads (ln_post / ln_final -> projection -> L2 normalise) with their backward.
+// Reference: retrieval/models/clip/model.py:154-160 (LayerNorm in fp32), :227-259 (VisionTransformer.forward),
+// retrieval/models/clip/prompt_learner.py:52-63,128-163 (TextEncoder / PromptLearner), retrieval/models/slinet.py:122,133.
+// All rows are [tokens, D] fp32 (residual stream) or bf16 (GEMM operands); one warp per row, 16-byte accesses.
+#include "ptx.cuh"
+#include "lpi_internal.h"
+
+namespace lpi {
+
+
+struct RowStats { float mean, rstd; };
+
+// mean / rstd of one row held as v[n] per lane (n = D/32 values, strided by 32 float4 groups)
+template <int NV>   // NV float4 per lane
+__device__ __forceinline__ RowStats row_stats(const float4 (&v)[NV], int D, float eps) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s += v[i].x + v[i].y + v[i].z + v[i].w;
+    const float mean = warp_sum(s) / D;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+        q += a * a + b * b + c * c + d * d;
+    }
+    const float var = warp_sum(q) / D;       // biased variance, two-pass (as torch native_layer_norm)
+    return {mean, rsqrtf(var + eps)};
+}
+
+template <int NV>
+__device__ __forceinline__ void ln_apply_store(const float4 (&v)[NV], RowStats st, const float* gamma, const float* beta, int lane,
+                                               float* out_f32, __nv_bfloat16* out_bf16) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        const float4 g = *reinterpret_cast<const float4*>(gamma + c), b = *reinterpret_cast<const float4*>(beta + c);
+        float4 y;
+        y.x = (v[i].x - st.mean) * st.rstd * g.x + b.x;
+        y.y = (v[i].y - st.mean) * st.rstd * g.y + b.y;
+        y.z = (v[i].z - st.mean) * st.rstd * g.z + b.z;
+        y.w = (v[i].w - st.mean) * st.rstd * g.w + b.w;
+        if (out_f32) *reinterpret_cast<float4*>(out_f32 + c) = y;
+        if (out_bf16) *reinterpret_cast<uint2*>(out_bf16 + c) = make_uint2(pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm
+template <int NV>
+__global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                     float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16, long M, int D, float eps) {
+    const long row = (long(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (row >= M) return;
+    const int lane = threadIdx.x & 31;
+    float4 v[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) v[i] = *reinterpret_cast<const float4*>(x + row * D + (i * 32 + lane) * 4);
+    const RowStats st = row_stats<NV>(v, D, eps);
+    ln_apply_store<NV>(v, st, gamma, beta, lane, out_f32 ? out_f32 + row * D : nullptr, out_bf16 ? out_bf16 + row * D : nullptr);
+}
+
+// dx = rstd * (gdy - mean(gdy) - xhat * mean(gdy * xhat)),  gdy = gamma * dy;   g = (accumulate ? g : 0) + dx
+template <int NV>
+__device__ __forceinline__ void ln_bwd_row(const float4 (&xv)[NV], const float4 (&dyv)[NV], const float* gamma, int D, float eps, int lane,
+                                           float4 (&dx)[NV]) {
+    const RowStats st = row_stats<NV>(xv, D, eps);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const float4 g = *reinterpret_cast<const float4*>(gamma + (i * 32 + lane) * 4);
+        float4 a;
+        a.x = g.x * dyv[i].x; a.y = g.y * dyv[i].y; a.z = g.z * dyv[i].z; a.w = g.w * dyv[i].w;
+        float4 h;
+        h.x = (xv[i].x - st.mean) * st.rstd; h.y = (xv[i].y - st.mean) * st.rstd;
+        h.z = (xv[i].z - st.mean) * st.rstd; h.w = (xv[i].w - st.mean) * st.rstd;
+        s1 += a.x + a.y + a.z + a.w;
+        s2 += a.x * h.x + a.y * h.y + a.z * h.z + a.w * h.w;
+        dx[i] = a;
+    }
+    s1 = warp_sum(s1) / D;
+    s2 = warp_sum(s2) / D;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        dx[i].x = st.rstd * (dx[i].x - s1 - (xv[i].x - st.mean) * st.rstd * s2);
+        dx[i].y = st.rstd * (dx[i].y - s1 - (xv[i].y - st.mean) * st.rstd * s2);
+        dx[i].z = st.rstd * (dx[i].z - s1 - (xv[i].z - st.mean) * st.rstd * s2);
+        dx[i].w = st.rstd * (dx[i].w - s1 - (xv[i].w - st.mean) * st.rstd * s2);
+    }
+}
+
+template <int NV>
+__global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
+                                     float* __restrict__ g, __nv_bfloat16* __restrict__ g_bf16, long M, int D, float eps, int accumulate) {
+    const long row = (long(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (row >= M) return;
+    const int lane = threadIdx.x & 31;
+    float4 xv[NV], dyv[NV], dx[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const long o = row * D + (i * 32 + lane) * 4;
+        xv[i] = *reinterpret_cast<const float4*>(x + o);
+        dyv[i] = *reinterpret_cast<const float4*>(dy + o);
+    }
+    ln_bwd_row<NV>(xv, dyv, gamma, D, eps, lane, dx);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const long o = row * D + (i * 32 + lane) * 4;
+        float4 r = dx[i];
+        if (accumulate) {
+            const float4 p = *reinterpret_cast<const float4*>(g + o);
+            r.x += p.x; r.y += p.y; r.z += p.z; r.w += p.w;
+        }
+        *reinterpret_cast<float4*>(g + o) = r;
+        if (g_bf16) *reinterpret_cast<uint2*>(g_bf16 + o) = make_uint2(pack_bf16x2(r.x, r.y), pack_bf16x2(r.z, r.w));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ vision front end
+// images [B,3,R,R] fp32 -> patch rows [B*G*G, 3*P*P] bf16, column = c*P*P + i*P + j (conv1.weight.view(D,-1) order)
+__global__ void im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int R, int P) {
+    const int G = R / P, K = 3 * P * P;
+    const long n = long(B) * G * G * K / 4;          // 4 consecutive j per thread (P % 4 == 0)
+    const long t = long(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const long e = t * 4;
+    const int col = int(e % K);
+    const long prow = e / K;
+    const int gx = int(prow % G), gy = int((prow / G) % G), b = int(prow / (G * G));
+    const int c = col / (P * P), i = (col / P) % P, j = col % P;
+    const float4 v = *reinterpret_cast<const float4*>(img + ((long(b) * 3 + c) * R + gy * P + i) * R + gx * P + j);
+    *reinterpret_cast<uint2*>(out + e) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+}
+
+// Token assembly + ln_pre (model.py:235-250).  Row l of sample b:
+//   l = 0          : class_embedding + pos[0]
+//   1 <= l <= P    : prompt_table[sel[b]][l-1]              (NO positional term)
+//   l > P          : patch_emb[b, l-1-P] + pos[l-P]
+template <int NV>
+__global__ void assemble_vision_kernel(const float* __restrict__ patch_emb, const float* __restrict__ cls, const float* __restrict__ pos,
+                                       const float* __restrict__ prompt_table, const int* __restrict__ sel, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, float* __restrict__ x_out, int B, int n_patch, int P, int D, float eps) {
+    const int L = 1 + P + n_patch;
+    const long row = (long(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (row >= long(B) * L) return;
+    const int lane = threadIdx.x & 31;
+    const int b = int(row / L), l = int(row % L);
+    float4 v[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = (i * 32 + lane) * 4;
+        if (l == 0) {
+            const float4 a = *reinterpret_cast<const float4*>(cls + c), p = *reinterpret_cast<const float4*>(pos + c);
+            v[i] = make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w);
+        } else if (l <= P) {
+            const int t = sel ? sel[b] : 0;
+            v[i] = *reinterpret_cast<const float4*>(prompt_table + (long(t) * P + (l - 1)) * D + c);
+        } else {
+            const float4 a = *reinterpret_cast<const float4*>(patch_emb + (long(b) * n_patch + (l - 1 - P)) * D + c);
+            const float4 p = *reinterpret_cast<const float4*>(pos + long(l - P) * D + c);
+            v[i] = make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w);
+        }
+    }
+    const RowStats st = row_stats<NV>(v, D, eps);
+    ln_apply_store<NV>(v, st, gamma, beta, lane, x_out + row * D, nullptr);
+}
+
+// d prompt_table[t, p, :] = sum over {b : sel[b] == t} of LNbwd(g[b, 1+p, :]; x = prompt_table[t, p, :])
+// grid = (P, T); each warp walks a strided slice of the batch, block-level reduction in shared memory (deterministic).
+template <int NV>
+__global__ void assemble_vision_bwd_kernel(const float* __restrict__ g, const float* __restrict__ prompt_table, const int* __restrict__ sel,
+                                           const float* __restrict__ gamma, float* __restrict__ d_prompt, int B, int L, int P, int D, float eps) {
+    extern __shared__ float red[];                   // [warps][D]
+    const int p = blockIdx.x, t = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    float4 xv[NV], acc[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        xv[i] = *reinterpret_cast<const float4*>(prompt_table + (long(t) * P + p) * D + (i * 32 + lane) * 4);
+        acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int b = warp; b < B; b += nw) {
+        if (sel && sel[b] != t) continue;
+        if (!sel && t != 0) continue;
+        float4 dyv[NV], dx[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) dyv[i] = *reinterpret_cast<const float4*>(g + (long(b) * L + 1 + p) * D + (i * 32 + lane) * 4);
+        ln_bwd_row<NV>(xv, dyv, gamma, D, eps, lane, dx);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) { acc[i].x += dx[i].x; acc[i].y += dx[i].y; acc[i].z += dx[i].z; acc[i].w += dx[i].w; }
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) *reinterpret_cast<float4*>(red + warp * D + (i * 32 + lane) * 4) = acc[i];
+    __syncthreads();
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+        float s = 0.f;
+        for (int w = 0; w < nw; ++w) s += red[w * D + c];
+        d_prompt[(long(t) * P + p) * D + c] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ text front end
+// x[b, l] = (l in [1, P] and ctx given ? ctx_table[sel[b]][l-1] : token_embedding[tok[b, l]]) + pos[l]
+__global__ void assemble_text_kernel(const float* __restrict__ emb, const long long* __restrict__ tok, const float* __restrict__ pos,
+                                     const float* __restrict__ ctx_table, const int* __restrict__ sel, float* __restrict__ x_out, int B, int L,
+                                     int P, int D) {
+    const long row = (long(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    if (row >= long(B) * L) return;
+    const int lane = threadIdx.x & 31;
+    const int b = int(row / L), l = int(row % L);
+    const float* src;
+    if (ctx_table && l >= 1 && l <= P) src = ctx_table + (long(sel ? sel[b] : 0) * P + (l - 1)) * D;
+    else src = emb + long(tok[row]) * D;
+    for (int c = lane * 4; c < D; c += 128) {
+        const float4 a = *reinterpret_cast<const float4*>(src + c), p = *reinterpret_cast<const float4*>(pos + long(l) * D + c);
+        *reinterpret_cast<float4*>(x_out + row * D + c) = make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w);
+    }
+}
+
+// d ctx_table[t, p, :] = sum over {b : sel[b] == t} g[b, 1+p, :]        grid = (P, T), thread per column
+__global__ void assemble_text_bwd_kernel(const float* __restrict__ g, const int* __restrict__ sel, float* __restrict__ d_ctx, int B, int L, int P,
+                                         int D) {
+    const int p = blockIdx.x, t = blockIdx.y;
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+        float s = 0.f;
+        for (int b = 0; b < B; ++b)
+            if ((sel ? sel[b] : 0) == t) s += g[(long(b) * L + 1 + p) * D + c];
+        d_ctx[(long(t) * P + p) * D + c] = s;
+    }
+}
+
+// Deep-prompt injection (the *intended* semantics of model.py:190-193, opt-in): x[b, 1+p, :] += prompt[sel[b], p, :]
+__global__ void inject_prompt_rows_kernel(float* __restrict__ x, const float* __restrict__ prompt, const int* __restrict__ sel, int B, int L, int P,
+                                          int D) {
+    const long e = (long(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+    if (e >= long(B) * P * D) return;
+    const int c = int(e % D), p = int((e / D) % P), b = int(e / (long(D) * P));
+    const float4 a = *reinterpret_cast<const float4*>(prompt + (long(sel ? sel[b] : 0) * P + p) * D + c);
+    float4* dst = reinterpret_cast<float4*>(x + (long(b) * L + 1 + p) * D + c);
+    float4 v = *dst;
+    v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+    *dst = v;
+}
+
+// ------------------------------------------------------------------------------------------------ encoder heads
+// feat[b] = normalize( LN(x[row_idx[b]]) @ proj ),  proj [D, E] row-major (model.py:254-257, prompt_learner.py:57-61, slinet.py:122,133)
+// One block (256 threads) per HB samples so the projection matrix is read once per HB rows.
+constexpr int HB = 4;
+__global__ void __launch_bounds__(256)
+head_fwd_kernel(const float* __restrict__ x, const int* __restrict__ row_idx, const float* __restrict__ gamma, const float* __restrict__ beta,
+                const float* __restrict__ proj, float* __restrict__ z_out, float* __restrict__ feat_out, int B, int D, int E, float eps) {
+    extern __shared__ float sm[];                    // y[HB][D] | red[HB][8]
+    float* y = sm;
+    float* red = sm + HB * D;
+    const int b0 = blockIdx.x * HB;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp < HB && b0 + warp < B) {                // one warp normalises one row
+        const float* xr = x + long(row_idx[b0 + warp]) * D;
+        float s = 0.f;
+        for (int c = lane; c < D; c += 32) s += xr[c];
+        const float mean = warp_sum(s) / D;
+        float q = 0.f;
+        for (int c = lane; c < D; c += 32) { const float d = xr[c] - mean; q += d * d; }
+        const float rstd = rsqrtf(warp_sum(q) / D + eps);
+        for (int c = lane; c < D; c += 32) y[warp * D + c] = (xr[c] - mean) * rstd * gamma[c] + beta[c];
+    } else if (warp < HB) {
+        for (int c = lane; c < D; c += 32) y[warp * D + c] = 0.f;
+    }
+    __syncthreads();
+    float ss[HB];
+#pragma unroll
+    for (int h = 0; h < HB; ++h) ss[h] = 0.f;
+    for (int e = threadIdx.x; e < E; e += 256) {
+        float acc[HB];
+#pragma unroll
+        for (int h = 0; h < HB; ++h) acc[h] = 0.f;
+        for (int k = 0; k < D; ++k) {
+            const float w = proj[long(k) * E + e];
+#pragma unroll
+            for (int h = 0; h < HB; ++h) acc[h] = fmaf(y[h * D + k], w, acc[h]);
+        }
+#pragma unroll
+        for (int h = 0; h < HB; ++h) {
+            if (b0 + h < B) z_out[long(b0 + h) * E + e] = acc[h];
+            ss[h] += acc[h] * acc[h];
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < HB; ++h) {
+        const float v = warp_sum(ss[h]);
+        if (lane == 0) red[h * 8 + warp] = v;
+    }
+    __syncthreads();
+    for (int h = 0; h < HB; ++h) {
+        if (b0 + h >= B) break;
+        float tot = 0.f;
+        for (int w = 0; w < 8; ++w) tot += red[h * 8 + w];
+        const float inv = 1.f / sqrtf(tot);
+        for (int e = threadIdx.x; e < E; e += 256) feat_out[long(b0 + h) * E + e] = z_out[long(b0 + h) * E + e] * inv;
+    }
+}
+
+// Backward of the head for one sample per block: (dfeat -> dz via the L2-norm backward) + dz_direct -> dy = dz @ proj^T
+// -> LN bwd -> g[row] (assigned).  dfeat = gradient wrt the normalised feature, dz_direct = gradient wrt the raw projection
+// (what VisionTransformer.forward / TextEncoder.forward return in the reference); either may be NULL.
+__global__ void __launch_bounds__(256)
+head_bwd_kernel(const float* __restrict__ dfeat, const float* __restrict__ dz_direct, const float* __restrict__ z, const float* __restrict__ x,
+                const int* __restrict__ row_idx, const float* __restrict__ gamma, const float* __restrict__ proj, float* __restrict__ g,
+                __nv_bfloat16* __restrict__ g_bf16, int D, int E, float eps) {
+    extern __shared__ float sm[];                    // dz[E] | dy[D] | red[16]
+    float* dz = sm;
+    float* dy = sm + E;
+    float* red = dy + D;
+    const int b = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* zr = z + long(b) * E;
+    const float* dfr = dfeat ? dfeat + long(b) * E : nullptr;
+    float a = 0.f, c = 0.f;
+    for (int e = threadIdx.x; e < E; e += 256) { a += zr[e] * zr[e]; c += dfr ? zr[e] * dfr[e] : 0.f; }
+    a = warp_sum(a); c = warp_sum(c);
+    if (lane == 0) { red[warp] = a; red[8 + warp] = c; }
+    __syncthreads();
+    float nn = 0.f, zd = 0.f;
+    for (int w = 0; w < 8; ++w) { nn += red[w]; zd += red[8 + w]; }
+    const float inv = 1.f / sqrtf(nn);
+    // f = z*inv ; dz = (df - f (f.df)) * inv ,  f.df = zd * inv
+    for (int e = threadIdx.x; e < E; e += 256) {
+        float v = dfr ? (dfr[e] - zr[e] * inv * (zd * inv)) * inv : 0.f;
+        if (dz_direct) v += dz_direct[long(b) * E + e];
+        dz[e] = v;
+    }
+    __syncthreads();
+    for (int k = warp; k < D; k += 8) {              // dy[k] = sum_e dz[e] proj[k, e]  (warp per k, coalesced over e)
+        float s = 0.f;
+        for (int e = lane; e < E; e += 32) s = fmaf(dz[e], proj[long(k) * E + e], s);
+        s = warp_sum(s);
+        if (lane == 0) dy[k] = s;
+    }
+    __syncthreads();
+    // LN backward over the row (block-wide)
+    const long row = row_idx[b];
+    const float* xr = x + row * D;
+    float s = 0.f;
+    for (int k = threadIdx.x; k < D; k += 256) s += xr[k];
+    s = warp_sum(s);
+    __syncthreads();
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    float mean = 0.f;
+    for (int w = 0; w < 8; ++w) mean += red[w];
+    mean /= D;
+    float q = 0.f;
+    for (int k = threadIdx.x; k < D; k += 256) { const float d = xr[k] - mean; q += d * d; }
+    q = warp_sum(q);
+    __syncthreads();
+    if (lane == 0) red[warp] = q;
+    __syncthreads();
+    float var = 0.f;
+    for (int w = 0; w < 8; ++w) var += red[w];
+    const float rstd = rsqrtf(var / D + eps);
+    float s1 = 0.f, s2 = 0.f;
+    for (int k = threadIdx.x; k < D; k += 256) {
+        const float gd = gamma[k] * dy[k];
+        s1 += gd;
+        s2 += gd * (xr[k] - mean) * rstd;
+    }
+    s1 = warp_sum(s1); s2 = warp_sum(s2);
+    __syncthreads();
+    if (lane == 0) { red[warp] = s1; red[8 + warp] = s2; }
+    __syncthreads();
+    float m1 = 0.f, m2 = 0.f;
+    for (int w = 0; w < 8; ++w) { m1 += red[w]; m2 += red[8 + w]; }
+    m1 /= D; m2 /= D;
+    for (int k = threadIdx.x; k < D; k += 256) {
+        const float v = rstd * (gamma[k] * dy[k] - m1 - (xr[k] - mean) * rstd * m2);
+        g[row * D + k] = v;
+        if (g_bf16) g_bf16[row * D + k] = __float2bfloat16_rn(v);
+    }
+}
+
+template <typename F>
+static int dispatch_nv(int D, F f) {
+    switch (D) {
+        case 512: return f(std::integral_constant<int, 4>{});
+        case 768: return f(std::integral_constant<int, 6>{});
+        case 1024: return f(std::integral_constant<int, 8>{});
+        case 256: return f(std::integral_constant<int, 2>{});
+        case 128: return f(std::integral_constant<int, 1>{});
+    }
+    return set_error(LPI_ERR_UNSUPPORTED, "row width D=%d not supported (128, 256, 512, 768, 1024)", D);
+}
+
+}  // namespace lpi
+
+using namespace lpi;
+
+static inline unsigned warp_grid(long rows, int threads) { return unsigned((rows * 32 + threads - 1) / threads); }
+
+extern "C" int lpi_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* out_f32, void* out_bf16, long long M, int D,
+                                 float eps, void* stream) {
+    if (M <= 0) return LPI_OK;
+    if (!out_f32 && !out_bf16) return set_error(LPI_ERR_ARG, "layernorm_fwd: no output");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc = dispatch_nv(D, [&](auto nv) {
+        layernorm_fwd_kernel<decltype(nv)::value><<<warp_grid(M, 256), 256, 0, st>>>(x, gamma, beta, out_f32,
+                                                                                       static_cast<__nv_bfloat16*>(out_bf16), M, D, eps);
+        return 0;
+    });
+    return rc ? rc : check_launch("layernorm_fwd");
+}
+
+extern "C" int lpi_layernorm_bwd(const float* dy, const float* x, const float* gamma, float* g, void* g_bf16, long long M, int D, float eps,
+                                 int accumulate, void* stream) {
+    if (M <= 0) return LPI_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc = dispatch_nv(D, [&](auto nv) {
+        layernorm_bwd_kernel<decltype(nv)::value><<<warp_grid(M, 128), 128, 0, st>>>(dy, x, gamma, g, static_cast<__nv_bfloat16*>(g_bf16), M,
+                                                                                       D, eps, accumulate);
+        return 0;
+    });
+    return rc ? rc : check_launch("layernorm_bwd");
+}
+
+extern "C" int lpi_im2col_patches(const float* images, void* out_bf16, int B, int resolution, int patch, void* stream) {
+    if (B <= 0) return LPI_OK;
+    if (patch % 4 || resolution % patch) return set_error(LPI_ERR_ARG, "im2col: bad resolution %d / patch %d", resolution, patch);
+    const int G = resolution / patch;
+    const long n = long(B) * G * G * 3 * patch * patch / 4;
+    im2col_kernel<<<unsigned((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(images, static_cast<__nv_bfloat16*>(out_bf16), B,
+                                                                                           resolution, patch);
+    return check_launch("im2col");
+}
+
+extern "C" int lpi_assemble_vision(const float* patch_emb, const float* cls, const float* pos, const float* prompt_table, const int* sel,
+                                   const float* ln_gamma, const float* ln_beta, float* x_out, int B, int n_patch, int P, int D, float eps,
+                                   void* stream) {
+    if (B <= 0) return LPI_OK;
+    if (P > 0 && !prompt_table) return set_error(LPI_ERR_ARG, "assemble_vision: P=%d but no prompt table", P);
+    const long rows = long(B) * (1 + P + n_patch);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc = dispatch_nv(D, [&](auto nv) {
+        assemble_vision_kernel<decltype(nv)::value><<<warp_grid(rows, 256), 256, 0, st>>>(patch_emb, cls, pos, prompt_table, sel, ln_gamma,
+                                                                                            ln_beta, x_out, B, n_patch, P, D, eps);
+        return 0;
+    });
+    return rc ? rc : check_launch("assemble_vision");
+}
+
+extern "C" int lpi_assemble_vision_bwd(const float* g, const float* prompt_table, const int* sel, const float* ln_gamma, float* d_prompt,
+                                       int B, int L, int P, int n_tables, int D, float eps, void* stream) {
+    if (B <= 0 || P <= 0) return LPI_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int threads = 512;
+    int rc = dispatch_nv(D, [&](auto nv) {
+        assemble_vision_bwd_kernel<decltype(nv)::value><<<dim3(P, n_tables), threads, (threads / 32) * D * sizeof(float), st>>>(
+            g, prompt_table, sel, ln_gamma, d_prompt, B, L, P, D, eps);
+        return 0;
+    });
+    return rc ? rc : check_launch("assemble_vision_bwd");
+}
+
+extern "C" int lpi_assemble_text(const float* token_embedding, const long long* tokens, const float* pos, const float* ctx_table,
+                                 const int* sel, float* x_out, int B, int L, int P, int D, void* stream) {
+    if (B <= 0) return LPI_OK;
+    if (D % 128) return set_error(LPI_ERR_ARG, "assemble_text: D=%d must be a multiple of 128", D);
+    assemble_text_kernel<<<warp_grid(long(B) * L, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(token_embedding, tokens, pos, ctx_table,
+                                                                                                      sel, x_out, B, L, P, D);
+    return check_launch("assemble_text");
+}
+
+extern "C" int lpi_assemble_text_bwd(const float* g, const int* sel, float* d_ctx, int B, int L, int P, int n_tables, int D, void* stream) {
+    if (B <= 0 || P <= 0) return LPI_OK;
+    assemble_text_bwd_kernel<<<dim3(P, n_tables), 256, 0, static_cast<cudaStream_t>(stream)>>>(g, sel, d_ctx, B, L, P, D);
+    return check_launch("assemble_text_bwd");
+}
+
+extern "C" int lpi_inject_prompt_rows(float* x, const float* prompt, const int* sel, int B, int L, int P, int D, void* stream) {
+    if (B <= 0 || P <= 0) return LPI_OK;
+    if (D % 4) return set_error(LPI_ERR_ARG, "inject_prompt_rows: D=%d must be a multiple of 4", D);
+    const long n = long(B) * P * D / 4;
+    inject_prompt_rows_kernel<<<unsigned((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(x, prompt, sel, B, L, P, D);
+    return check_launch("inject_prompt_rows");
+}
+
+extern "C" int lpi_head_fwd(const float* x, const int* row_idx, const float* ln_gamma, const float* ln_beta, const float* proj, float* z_out,
+                            float* feat_out, int B, int D, int E, float eps, void* stream) {
+    if (B <= 0) return LPI_OK;
+    const int smem = (HB * D + HB * 8) * sizeof(float);
+    head_fwd_kernel<<<(B + HB - 1) / HB, 256, smem, static_cast<cudaStream_t>(stream)>>>(x, row_idx, ln_gamma, ln_beta, proj, z_out, feat_out,
+                                                                                        B, D, E, eps);
+    return check_launch("head_fwd");
+}
+
+extern "C" int lpi_head_bwd(const float* dfeat, const float* dz_direct, const float* z, const float* x, const int* row_idx,
+                            const float* ln_gamma, const float* proj, float* g, void* g_bf16, int B, int D, int E, float eps, void* stream) {
+    if (B <= 0) return LPI_OK;
+    if (!dfeat && !dz_direct) return set_error(LPI_ERR_ARG, "head_bwd: no upstream gradient");
+    const int smem = (E + D + 16) * sizeof(float);
+    head_bwd_kernel<<<B, 256, smem, static_cast<cudaStream_t>(stream)>>>(dfeat, dz_direct, z, x, row_idx, ln_gamma, proj, g,
+                                                                         static_cast<__nv_bfloat16*>(g_bf16), D, E, eps);
+    return check_launch("head_bwd");
+}

@@ -135,9 +135,10 @@ __global__ void recall_counts_kernel(const int* __restrict__ topk, int nq, int k
     if (rank_out) rank_out[q] = rank;
     const int t = task ? task[q] : 0;
     if (t >= 0 && t < n_tasks) {
-        if (rank < 1) atomicAdd(&counts[4 * t + 0], 1);
-        if (rank < 5) atomicAdd(&counts[4 * t + 1], 1);
-        if (rank < 10) atomicAdd(&counts[4 * t + 2], 1);
+        const bool found = rank < k;           // a ground truth outside the kept top-k never counts as a hit
+        if (found && rank < 1) atomicAdd(&counts[4 * t + 0], 1);
+        if (found && rank < 5) atomicAdd(&counts[4 * t + 1], 1);
+        if (found && rank < 10) atomicAdd(&counts[4 * t + 2], 1);
         atomicAdd(&counts[4 * t + 3], 1);
     }
 }

@@ -1,0 +1,264 @@
+"""Tower executor: sequences the sm_100a kernels of liblpi_b200.so for the prompted CLIP ViT-B/16 image tower and the
+12-layer text transformer, forward and backward (dgrad only -- every CLIP weight is frozen in LPI, sprompt.py:229-237,
+so there is no wgrad and GEMM inputs need not be kept).
+
+Reference maths: retrieval/models/clip/model.py:168-259 (ResidualAttentionBlock, Transformer, VisionTransformer),
+retrieval/models/clip/prompt_learner.py:52-63 (TextEncoder).  Layout here is batch-major tokens [B*L, D]
+(the reference permutes to [L, B, D]; the maths is layout independent).
+
+Precision plan (SURVEY.md section 7 error budget): bf16 GEMM/attention operands, fp32 accumulation, fp32 residual stream,
+fp32 LayerNorm statistics, fp32 gradient stream with a bf16 shadow as the A operand of the next dgrad GEMM, fp32 heads.
+torch is used for buffers and streams only.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import ops
+
+
+@dataclass
+class BlockWeights:
+    ln1_g: torch.Tensor
+    ln1_b: torch.Tensor
+    ln2_g: torch.Tensor
+    ln2_b: torch.Tensor
+    w_in: torch.Tensor          # [3D, D] bf16   (and its transpose for dgrad)
+    w_in_t: torch.Tensor        # [D, 3D]
+    b_in: torch.Tensor          # [3D] fp32
+    w_out: torch.Tensor         # [D, D]
+    w_out_t: torch.Tensor
+    b_out: torch.Tensor
+    w_fc: torch.Tensor          # [4D, D]
+    w_fc_t: torch.Tensor        # [D, 4D]
+    b_fc: torch.Tensor
+    w_proj: torch.Tensor        # [D, 4D]
+    w_proj_t: torch.Tensor      # [4D, D]
+    b_proj: torch.Tensor
+
+
+def _bf16(t: torch.Tensor, dev) -> torch.Tensor:
+    return t.detach().to(dev, torch.float32).to(torch.bfloat16).contiguous()
+
+
+def _f32(t: torch.Tensor, dev) -> torch.Tensor:
+    return t.detach().to(dev, torch.float32).contiguous()
+
+
+def load_blocks(sd: Dict[str, torch.Tensor], prefix: str, dev, need_grad: bool = True) -> List[BlockWeights]:
+    """`prefix` = 'visual.transformer.resblocks.' or 'transformer.resblocks.' in a CLIP state_dict."""
+    blocks = []
+    i = 0
+    while f"{prefix}{i}.ln_1.weight" in sd:
+        p = f"{prefix}{i}."
+        g = lambda k: sd[p + k]
+        def pair(k):
+            w = _bf16(g(k), dev)
+            return w, (w.t().contiguous() if need_grad else None)
+        w_in, w_in_t = pair("attn.in_proj_weight")
+        w_out, w_out_t = pair("attn.out_proj.weight")
+        w_fc, w_fc_t = pair("mlp.c_fc.weight")
+        w_proj, w_proj_t = pair("mlp.c_proj.weight")
+        blocks.append(BlockWeights(
+            ln1_g=_f32(g("ln_1.weight"), dev), ln1_b=_f32(g("ln_1.bias"), dev), ln2_g=_f32(g("ln_2.weight"), dev),
+            ln2_b=_f32(g("ln_2.bias"), dev), w_in=w_in, w_in_t=w_in_t, b_in=_f32(g("attn.in_proj_bias"), dev), w_out=w_out,
+            w_out_t=w_out_t, b_out=_f32(g("attn.out_proj.bias"), dev), w_fc=w_fc, w_fc_t=w_fc_t, b_fc=_f32(g("mlp.c_fc.bias"), dev),
+            w_proj=w_proj, w_proj_t=w_proj_t, b_proj=_f32(g("mlp.c_proj.bias"), dev)))
+        i += 1
+    return blocks
+
+
+@dataclass
+class BlockSaved:
+    x: torch.Tensor             # block input, fp32 [M, D]
+    x1: torch.Tensor            # after the attention residual, fp32
+    qkv: torch.Tensor           # bf16 [M, 3D]
+    o: torch.Tensor             # attention output, bf16 [M, D]
+    lse: torch.Tensor
+    z: torch.Tensor             # c_fc pre-activation, bf16 [M, 4D]
+
+
+@dataclass
+class TowerTape:
+    B: int
+    L: int
+    blocks: List[BlockSaved] = field(default_factory=list)
+    x_final: Optional[torch.Tensor] = None
+    injected: Dict[int, bool] = field(default_factory=dict)
+
+
+class Tower:
+    """12 pre-LN residual attention blocks (model.py:187-196) over a [B*L, D] fp32 residual stream."""
+
+    def __init__(self, sd, prefix: str, heads: int, causal: bool, dev, need_grad: bool = True):
+        self.blocks = load_blocks(sd, prefix, dev, need_grad)
+        self.heads = heads
+        self.causal = causal
+        self.width = heads * 64
+        self.dev = dev
+
+    # -------------------------------------------------------------------------------------------- forward
+    def forward(self, x: torch.Tensor, B: int, L: int, tape: Optional[TowerTape] = None,
+                inject: Optional[dict] = None) -> torch.Tensor:
+        """x fp32 [B*L, D] (consumed).  `inject` = {'layers': {l,...}, 'table': [T, Lp, P, D] fp32, 'sel': int32[B] or None, 'P': P}
+        adds table[sel[b], l] to rows 1..P before block l (opt-in deep-prompt injection, l >= 1)."""
+        H = self.heads
+        for li, w in enumerate(self.blocks):
+            if inject is not None and li != 0 and li in inject["layers"]:
+                ops.inject_prompt_rows(x, inject["table"][:, li].contiguous(), inject["sel"], B, L, inject["P"], self.width)
+            _, h = ops.layernorm_fwd(x, w.ln1_g, w.ln1_b)
+            qkv = ops.gemm(h, w.w_in, ops.EPI_BIAS_BF16, bias=w.b_in)
+            o, lse = ops.attn_fwd(qkv, B, L, H, self.causal, want_lse=tape is not None)
+            if tape is not None:
+                x1 = ops.gemm(o, w.w_out, ops.EPI_BIAS_RESID_F32, bias=w.b_out, resid=x)
+            else:
+                x1 = ops.gemm(o, w.w_out, ops.EPI_BIAS_RESID_F32, bias=w.b_out, resid=x, out=x)      # in place
+            _, h2 = ops.layernorm_fwd(x1, w.ln2_g, w.ln2_b)
+            z = torch.empty(x.shape[0], 4 * self.width, device=x.device, dtype=torch.bfloat16) if tape is not None else None
+            a = ops.gemm(h2, w.w_fc, ops.EPI_BIAS_GELU_BF16, bias=w.b_fc, out2=z)
+            if tape is not None:
+                x2 = ops.gemm(a, w.w_proj, ops.EPI_BIAS_RESID_F32, bias=w.b_proj, resid=x1)
+                tape.blocks.append(BlockSaved(x=x, x1=x1, qkv=qkv, o=o, lse=lse, z=z))
+            else:
+                x2 = ops.gemm(a, w.w_proj, ops.EPI_BIAS_RESID_F32, bias=w.b_proj, resid=x1, out=x1)
+            x = x2
+        if tape is not None:
+            tape.x_final = x
+        return x
+
+    # -------------------------------------------------------------------------------------------- backward
+    def backward(self, tape: TowerTape, g: torch.Tensor, g_bf16: torch.Tensor, inject: Optional[dict] = None,
+                 inject_grads: Optional[dict] = None) -> torch.Tensor:
+        """g fp32 [B*L, D] = d loss / d (tower output), updated in place down to d loss / d (tower input);
+        g_bf16 is its bf16 shadow (must match g on entry).  With `inject`, inject_grads[l] receives
+        sum_b g_l[b, 1:P+1] for every injected layer."""
+        B, L, H = tape.B, tape.L, self.heads
+        for li in range(len(self.blocks) - 1, -1, -1):
+            w, s = self.blocks[li], tape.blocks[li]
+            dz = ops.gemm(g_bf16, w.w_proj_t, ops.EPI_DGELU_BF16, aux=s.z)
+            dh2 = ops.gemm(dz, w.w_fc_t, ops.EPI_F32)
+            ops.layernorm_bwd(dh2, s.x1, w.ln2_g, g, g_bf16, accumulate=True)
+            do = ops.gemm(g_bf16, w.w_out_t, ops.EPI_BF16)
+            dqkv = ops.attn_bwd(s.qkv, s.o, do, s.lse, B, L, H, self.causal)
+            dh1 = ops.gemm(dqkv, w.w_in_t, ops.EPI_F32)
+            ops.layernorm_bwd(dh1, s.x, w.ln1_g, g, g_bf16, accumulate=True)
+            if inject is not None and li != 0 and li in inject["layers"] and inject_grads is not None:
+                n_tables = inject["table"].shape[0]
+                inject_grads[li] = ops.sum_prompt_rows(g, inject["sel"], B, L, inject["P"], n_tables, self.width)
+        return g
+
+
+# ------------------------------------------------------------------------------------------------ image encoder
+class VisionEngine:
+    """VisionTransformer.forward (model.py:227-259) on the kernels: im2col -> patch GEMM -> assemble(+ln_pre) -> tower -> head."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], dev, prefix: str = "visual.", need_grad: bool = True):
+        w = sd[prefix + "conv1.weight"]
+        self.width, _, self.patch, _ = w.shape
+        self.conv_w = _bf16(w.reshape(self.width, -1), dev)
+        self.cls = _f32(sd[prefix + "class_embedding"], dev)
+        self.pos = _f32(sd[prefix + "positional_embedding"], dev)
+        self.ln_pre = (_f32(sd[prefix + "ln_pre.weight"], dev), _f32(sd[prefix + "ln_pre.bias"], dev))
+        self.ln_post = (_f32(sd[prefix + "ln_post.weight"], dev), _f32(sd[prefix + "ln_post.bias"], dev))
+        self.proj = _f32(sd[prefix + "proj"], dev)
+        self.tower = Tower(sd, prefix + "transformer.resblocks.", self.width // 64, False, dev, need_grad)
+        self.n_patch = self.pos.shape[0] - 1
+        self.dev = dev
+
+    def forward(self, images: torch.Tensor, prompt_table: Optional[torch.Tensor] = None, sel: Optional[torch.Tensor] = None,
+                tape: Optional[dict] = None, inject_layers: Sequence[int] = ()):
+        """images [B,3,R,R] fp32; prompt_table [T, Lp, P, D] fp32 (layer 0 enters the token sequence, model.py:240-248) or None;
+        sel int32[B] picks the table per sample (None = table 0).  Returns (L2-normalised features, raw projection z), both [B, E] fp32."""
+        B = images.shape[0]
+        D = self.width
+        patches = ops.im2col_patches(images.contiguous(), self.patch)
+        pe = ops.gemm(patches, self.conv_w, ops.EPI_F32)
+        P = 0 if prompt_table is None else prompt_table.shape[2]
+        layer0 = None if prompt_table is None else prompt_table[:, 0].contiguous()
+        x = ops.assemble_vision(pe, self.cls, self.pos, layer0, sel, self.ln_pre[0], self.ln_pre[1], B, self.n_patch, P, D)
+        L = 1 + P + self.n_patch
+        inject = None
+        if prompt_table is not None and len(inject_layers) > 0:
+            inject = {"layers": set(int(l) for l in inject_layers), "table": prompt_table, "sel": sel, "P": P}
+        ttape = TowerTape(B, L) if tape is not None else None
+        x = self.tower.forward(x, B, L, ttape, inject)
+        rows = torch.arange(B, device=x.device, dtype=torch.int32) * L
+        feat, z = ops.head_fwd(x, rows, self.ln_post[0], self.ln_post[1], self.proj)
+        if tape is not None:
+            tape.update(dict(tower=ttape, rows=rows, z=z, x=x, layer0=layer0, sel=sel, P=P, L=L, B=B, inject=inject,
+                             n_tables=0 if prompt_table is None else prompt_table.shape[0], Lp=0 if prompt_table is None else prompt_table.shape[1]))
+        return feat, z
+
+    def backward(self, tape: dict, dfeat: Optional[torch.Tensor], dz: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+        """d loss / d prompt_table [T, Lp, P, D] (zero for layers that never entered the encoder).  dfeat = gradient wrt the
+        normalised feature, dz = gradient wrt the raw projection (either may be None)."""
+        B, L, D, P = tape["B"], tape["L"], self.width, tape["P"]
+        dev = tape["x"].device
+        g = torch.zeros(B * L, D, device=dev, dtype=torch.float32)
+        gb = torch.zeros(B * L, D, device=dev, dtype=torch.bfloat16)
+        ops.head_bwd(None if dfeat is None else dfeat.contiguous(), None if dz is None else dz.contiguous(), tape["z"], tape["x"],
+                     tape["rows"], self.ln_post[0], self.proj, g, gb)
+        inj_grads = {}
+        self.tower.backward(tape["tower"], g, gb, tape["inject"], inj_grads)
+        if P == 0:
+            return None
+        G = torch.zeros(tape["n_tables"], tape["Lp"], P, D, device=dev, dtype=torch.float32)
+        G[:, 0] = ops.assemble_vision_bwd(g, tape["layer0"], tape["sel"], self.ln_pre[0], B, L, P, tape["n_tables"], D)
+        for l, gl in inj_grads.items():
+            G[:, l] = gl
+        return G
+
+
+# ------------------------------------------------------------------------------------------------ text encoder
+class TextEngine:
+    """PromptLearner splice + TextEncoder.forward (prompt_learner.py:133-163, 52-63) on the kernels."""
+
+    def __init__(self, sd: Dict[str, torch.Tensor], dev, need_grad: bool = True):
+        self.emb = _f32(sd["token_embedding.weight"], dev)
+        self.pos = _f32(sd["positional_embedding"], dev)
+        self.ln_final = (_f32(sd["ln_final.weight"], dev), _f32(sd["ln_final.bias"], dev))
+        self.proj = _f32(sd["text_projection"], dev)
+        self.width = self.emb.shape[1]
+        self.tower = Tower(sd, "transformer.resblocks.", self.width // 64, True, dev, need_grad)
+        self.context_length = self.pos.shape[0]
+        self.dev = dev
+
+    def forward(self, tokens: torch.Tensor, prompt_table: Optional[torch.Tensor] = None, sel: Optional[torch.Tensor] = None,
+                tape: Optional[dict] = None, inject_layers: Sequence[int] = ()):
+        """tokens int64 [B, 77] on the device; prompt_table [T, Lp, P, Dt] fp32 (layer 0 is spliced over positions 1..P) or None."""
+        B, L = tokens.shape
+        D = self.width
+        P = 0 if prompt_table is None else prompt_table.shape[2]
+        layer0 = None if prompt_table is None else prompt_table[:, 0].contiguous()
+        x = ops.assemble_text(self.emb, tokens.contiguous(), self.pos, layer0, sel, B, L, P, D)
+        inject = None
+        if prompt_table is not None and len(inject_layers) > 0:
+            inject = {"layers": set(int(l) for l in inject_layers), "table": prompt_table, "sel": sel, "P": P}
+        ttape = TowerTape(B, L) if tape is not None else None
+        x = self.tower.forward(x, B, L, ttape, inject)
+        rows = (torch.arange(B, device=x.device, dtype=torch.int64) * L + tokens.argmax(dim=-1)).to(torch.int32)   # EOT row
+        feat, z = ops.head_fwd(x, rows, self.ln_final[0], self.ln_final[1], self.proj)
+        if tape is not None:
+            tape.update(dict(tower=ttape, rows=rows, z=z, x=x, sel=sel, P=P, L=L, B=B, inject=inject,
+                             n_tables=0 if prompt_table is None else prompt_table.shape[0], Lp=0 if prompt_table is None else prompt_table.shape[1]))
+        return feat, z
+
+    def backward(self, tape: dict, dfeat: Optional[torch.Tensor], dz: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
+        B, L, D, P = tape["B"], tape["L"], self.width, tape["P"]
+        dev = tape["x"].device
+        g = torch.zeros(B * L, D, device=dev, dtype=torch.float32)
+        gb = torch.zeros(B * L, D, device=dev, dtype=torch.bfloat16)
+        ops.head_bwd(None if dfeat is None else dfeat.contiguous(), None if dz is None else dz.contiguous(), tape["z"], tape["x"],
+                     tape["rows"], self.ln_final[0], self.proj, g, gb)
+        inj_grads = {}
+        self.tower.backward(tape["tower"], g, gb, tape["inject"], inj_grads)
+        if P == 0:
+            return None
+        G = torch.zeros(tape["n_tables"], tape["Lp"], P, D, device=dev, dtype=torch.float32)
+        G[:, 0] = ops.sum_prompt_rows(g, tape["sel"], B, L, P, tape["n_tables"], D)
+        for l, gl in inj_grads.items():
+            G[:, l] = gl
+        return G

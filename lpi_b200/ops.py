@@ -152,3 +152,233 @@ def l2_normalize(x: torch.Tensor, want_norm: bool = False):
     call("l2_normalize", ptr(x), n, dim, ptr(out), ptr(nrm), stream_ptr())
     _count()
     return (out, nrm) if want_norm else out
+
+
+# ------------------------------------------------------------------------------------------ attention
+def attn_fwd(qkv: torch.Tensor, B: int, L: int, H: int, causal: bool, want_lse: bool = True):
+    """qkv [B*L, 3*H*64] bf16 -> (out [B*L, H*64] bf16, lse2 [B*H*L] fp32 or None)."""
+    _lib.require_device()
+    _chk(qkv, torch.bfloat16, "qkv")
+    assert qkv.shape == (B * L, 3 * H * 64)
+    out = torch.empty(B * L, H * 64, device=qkv.device, dtype=torch.bfloat16)
+    lse = torch.empty(B * H * L, device=qkv.device, dtype=torch.float32) if want_lse else None
+    call("attn_fwd", ptr(qkv), ptr(out), ptr(lse), B, L, H, int(causal), stream_ptr())
+    _count()
+    return out, lse
+
+
+def attn_bwd(qkv, out, d_out, lse, B: int, L: int, H: int, causal: bool, dqkv: Optional[torch.Tensor] = None):
+    for t, n in ((qkv, "qkv"), (out, "out"), (d_out, "d_out")):
+        _chk(t, torch.bfloat16, n)
+    _chk(lse, torch.float32, "lse")
+    if dqkv is None:
+        dqkv = torch.empty_like(qkv)
+    delta = torch.empty(B * H * L, device=qkv.device, dtype=torch.float32)
+    call("attn_bwd", ptr(qkv), ptr(out), ptr(d_out), ptr(lse), ptr(delta), ptr(dqkv), B, L, H, int(causal), stream_ptr())
+    _count(3)
+    return dqkv
+
+
+# ------------------------------------------------------------------------------------------ LayerNorm / front ends / heads
+LN_EPS = 1e-5
+
+
+def layernorm_fwd(x, gamma, beta, want_f32=False, want_bf16=True):
+    _lib.require_device()
+    _chk(x, torch.float32, "x")
+    M, D = x.shape
+    of = torch.empty_like(x) if want_f32 else None
+    ob = torch.empty(M, D, device=x.device, dtype=torch.bfloat16) if want_bf16 else None
+    call("layernorm_fwd", ptr(x), ptr(gamma), ptr(beta), ptr(of), ptr(ob), C.c_longlong(M), D, C.c_float(LN_EPS), stream_ptr())
+    _count()
+    return of, ob
+
+
+def layernorm_bwd(dy, x, gamma, g, g_bf16=None, accumulate=True):
+    """g = (accumulate ? g : 0) + dLN(dy; x, gamma), in place; optional bf16 shadow."""
+    for t, n in ((dy, "dy"), (x, "x"), (g, "g")):
+        _chk(t, torch.float32, n)
+    M, D = x.shape
+    call("layernorm_bwd", ptr(dy), ptr(x), ptr(gamma), ptr(g), ptr(g_bf16), C.c_longlong(M), D, C.c_float(LN_EPS), int(accumulate),
+         stream_ptr())
+    _count()
+    return g
+
+
+def im2col_patches(images: torch.Tensor, patch: int) -> torch.Tensor:
+    _lib.require_device()
+    _chk(images, torch.float32, "images")
+    B, ch, R, _ = images.shape
+    assert ch == 3
+    G = R // patch
+    out = torch.empty(B * G * G, 3 * patch * patch, device=images.device, dtype=torch.bfloat16)
+    call("im2col_patches", ptr(images), ptr(out), B, R, patch, stream_ptr())
+    _count()
+    return out
+
+
+def assemble_vision(patch_emb, cls, pos, prompt_table, sel, ln_g, ln_b, B, n_patch, P, D):
+    x = torch.empty(B * (1 + P + n_patch), D, device=patch_emb.device, dtype=torch.float32)
+    call("assemble_vision", ptr(patch_emb), ptr(cls), ptr(pos), ptr(prompt_table), ptr(sel), ptr(ln_g), ptr(ln_b), ptr(x), B, n_patch, P, D,
+         C.c_float(LN_EPS), stream_ptr())
+    _count()
+    return x
+
+
+def assemble_vision_bwd(g, prompt_table, sel, ln_g, B, L, P, n_tables, D):
+    d = torch.empty(n_tables, P, D, device=g.device, dtype=torch.float32)
+    call("assemble_vision_bwd", ptr(g), ptr(prompt_table), ptr(sel), ptr(ln_g), ptr(d), B, L, P, n_tables, D, C.c_float(LN_EPS), stream_ptr())
+    _count()
+    return d
+
+
+def assemble_text(emb, tokens, pos, ctx_table, sel, B, L, P, D):
+    _lib.require_device()
+    _chk(tokens, torch.int64, "tokens")
+    x = torch.empty(B * L, D, device=emb.device, dtype=torch.float32)
+    call("assemble_text", ptr(emb), ptr(tokens), ptr(pos), ptr(ctx_table), ptr(sel), ptr(x), B, L, P, D, stream_ptr())
+    _count()
+    return x
+
+
+def sum_prompt_rows(g, sel, B, L, P, n_tables, D):
+    """d_table[t,p,:] = sum_{b: sel[b]=t} g[b,1+p,:]  (backward of the text splice and of deep-prompt injection)."""
+    d = torch.empty(n_tables, P, D, device=g.device, dtype=torch.float32)
+    call("assemble_text_bwd", ptr(g), ptr(sel), ptr(d), B, L, P, n_tables, D, stream_ptr())
+    _count()
+    return d
+
+
+def inject_prompt_rows(x, prompt, sel, B, L, P, D):
+    call("inject_prompt_rows", ptr(x), ptr(prompt), ptr(sel), B, L, P, D, stream_ptr())
+    _count()
+
+
+def head_fwd(x, row_idx, ln_g, ln_b, proj):
+    _chk(x, torch.float32, "x")
+    _chk(row_idx, torch.int32, "row_idx")
+    B = row_idx.shape[0]
+    D, E = proj.shape
+    z = torch.empty(B, E, device=x.device, dtype=torch.float32)
+    f = torch.empty(B, E, device=x.device, dtype=torch.float32)
+    call("head_fwd", ptr(x), ptr(row_idx), ptr(ln_g), ptr(ln_b), ptr(proj), ptr(z), ptr(f), B, D, E, C.c_float(LN_EPS), stream_ptr())
+    _count()
+    return f, z
+
+
+def head_bwd(dfeat, dz, z, x, row_idx, ln_g, proj, g, g_bf16=None):
+    for t, n in ((dfeat, "dfeat"), (dz, "dz")):
+        if t is not None:
+            _chk(t, torch.float32, n)
+    B = row_idx.shape[0]
+    D, E = proj.shape
+    call("head_bwd", ptr(dfeat), ptr(dz), ptr(z), ptr(x), ptr(row_idx), ptr(ln_g), ptr(proj), ptr(g), ptr(g_bf16), B, D, E, C.c_float(LN_EPS),
+         stream_ptr())
+    _count()
+
+
+# ------------------------------------------------------------------------------------------ DecomposedPrompt
+def prompt_fwd(d1, d2v, d2t, d3v, d3t):
+    _lib.require_device()
+    for t in (d1, d2v, d2t, d3v, d3t):
+        _chk(t, torch.float32, "factor")
+    L, r = d1.shape
+    P, Dv, Dt = d2v.shape[0], d3v.shape[0], d3t.shape[0]
+    vis = torch.empty(L, P, Dv, device=d1.device, dtype=torch.float32)
+    txt = torch.empty(L, P, Dt, device=d1.device, dtype=torch.float32)
+    call("prompt_fwd", ptr(d1), ptr(d2v), ptr(d2t), ptr(d3v), ptr(d3t), ptr(vis), ptr(txt), L, P, Dv, Dt, r, stream_ptr())
+    _count()
+    return vis, txt
+
+
+def prompt_bwd(d1, d2v, d2t, d3v, d3t, g_vis, g_txt):
+    _chk(g_vis, torch.float32, "g_vis")
+    _chk(g_txt, torch.float32, "g_txt")
+    L, r = d1.shape
+    P, Dv, Dt = d2v.shape[0], d3v.shape[0], d3t.shape[0]
+    ws = torch.empty(2 * L * P * r, device=d1.device, dtype=torch.float32)
+    outs = [torch.empty_like(t) for t in (d1, d2v, d2t, d3v, d3t)]
+    call("prompt_bwd", ptr(d1), ptr(d2v), ptr(d2t), ptr(d3v), ptr(d3t), ptr(g_vis), ptr(g_txt), ptr(ws), *[ptr(o) for o in outs], L, P, Dv,
+         Dt, r, stream_ptr())
+    _count(3)
+    return outs
+
+
+# ------------------------------------------------------------------------------------------ losses / optimiser
+def sgemm(a: torch.Tensor, b: torch.Tensor, alpha: float = 1.0, out: Optional[torch.Tensor] = None, beta: float = 0.0):
+    """out[M,N] = alpha * a[M,K] @ b[K,N] + beta*out for arbitrary-strided 2-D fp32 views (exact fp32 products)."""
+    _lib.require_device()
+    assert a.dtype == torch.float32 and b.dtype == torch.float32 and a.is_cuda and b.is_cuda
+    M, K = a.shape
+    K2, N = b.shape
+    assert K == K2
+    if out is None:
+        out = torch.empty(M, N, device=a.device, dtype=torch.float32)
+    call("sgemm_f32", ptr(a), ptr(b), ptr(out), M, N, K, C.c_longlong(a.stride(0)), C.c_longlong(a.stride(1)), C.c_longlong(b.stride(0)),
+         C.c_longlong(b.stride(1)), C.c_longlong(out.stride(0)), C.c_float(alpha), C.c_float(beta), stream_ptr())
+    _count()
+    return out
+
+
+def clip_loss_logits(logits: torch.Tensor, weight: float = 1.0, want_grad: bool = True):
+    """(loss[1], dlogits or None) of weight * 1/2 [CE(S, arange) + CE(S^T, arange)]."""
+    _lib.require_device()
+    _chk(logits, torch.float32, "logits")
+    n = logits.shape[0]
+    assert logits.shape == (n, n)
+    ws = torch.empty(2 * n, device=logits.device, dtype=torch.float32)
+    loss = torch.empty(1, device=logits.device, dtype=torch.float32)
+    d = torch.empty_like(logits) if want_grad else None
+    call("clip_loss_logits", ptr(logits), n, C.c_float(weight), ptr(ws), ptr(loss), ptr(d), stream_ptr())
+    _count(3 if want_grad else 2)
+    return loss, d
+
+
+def row_mean(x: torch.Tensor, scale: float = 1.0):
+    _chk(x, torch.float32, "x")
+    rows, D = x.shape
+    out = torch.empty(rows, device=x.device, dtype=torch.float32)
+    call("row_mean", ptr(x), ptr(out), rows, D, C.c_float(scale), stream_ptr())
+    _count()
+    return out
+
+
+def add_rowconst(G: torch.Tensor, v: torch.Tensor, alpha: float, accumulate: bool = True):
+    rows, D = G.shape
+    call("add_rowconst", ptr(G), ptr(v), C.c_longlong(rows), D, C.c_float(alpha), int(accumulate), stream_ptr())
+    _count()
+
+
+def task_loss(X: torch.Tensor, target: torch.Tensor, temperature: float, weight: float, loss_out: torch.Tensor, loss_accumulate: bool,
+              grad_last_row: Optional[torch.Tensor], grad_accumulate: bool = True, n_part: int = 64):
+    """nt_bxent_loss over rows of X [R,n]; loss_out (+)= weight*loss; grad_last_row (+)= d/dX[R-1]."""
+    _chk(X, torch.float32, "X")
+    _chk(target, torch.int32, "target")
+    R, n = X.shape
+    ws = torch.empty(n_part * R * R, device=X.device, dtype=torch.float32)
+    coef = torch.empty(R, device=X.device, dtype=torch.float32)
+    call("task_loss", ptr(X), R, C.c_longlong(n), ptr(target), C.c_float(temperature), C.c_float(weight), ptr(ws), n_part, ptr(loss_out),
+         int(loss_accumulate), ptr(coef), ptr(grad_last_row), int(grad_accumulate), stream_ptr())
+    _count(3 if grad_last_row is not None else 2)
+    return coef
+
+
+def sgd_momentum_step(w, g, v, lr, momentum, weight_decay, first_step):
+    for t, n in ((w, "w"), (g, "g"), (v, "v")):
+        _chk(t, torch.float32, n)
+    call("sgd_momentum_step", ptr(w), ptr(g), ptr(v), C.c_longlong(w.numel()), C.c_float(lr), C.c_float(momentum), C.c_float(weight_decay),
+         int(first_step), stream_ptr())
+    _count()
+
+
+def nearest_center_l1(feats: torch.Tensor, centers: torch.Tensor) -> torch.Tensor:
+    """feats [B,E], centers [T,C,E] fp32 -> int64 [B] (sprompt.py:336-368)."""
+    _lib.require_device()
+    _chk(feats, torch.float32, "feats")
+    _chk(centers, torch.float32, "centers")
+    B, E = feats.shape
+    T, Cn, _ = centers.shape
+    sel = torch.empty(B, device=feats.device, dtype=torch.int64)
+    call("nearest_center_l1", ptr(feats), ptr(centers), B, T, Cn, E, ptr(sel), stream_ptr())
+    _count()
+    return sel

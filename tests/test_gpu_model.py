@@ -1,0 +1,93 @@
+"""-m gpu end-to-end parity of the prompted-CLIP path: CUDA engine vs the golden fixtures generated from the REAL reference
+(tests/golden/make_golden.py, B = 4, seed 0, fp32 on CPU).  Tolerances are BASELINE.json's: embeddings / loss 1e-2 relative
+in bf16, prompt gradients 2e-2."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from lpi_b200 import lpi_step, ops, synthetic as S
+from lpi_b200.engine import TextEngine, VisionEngine
+from oracle import lpi_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return float((a.double().cpu() - b.double().cpu()).norm() / b.double().cpu().norm())
+
+
+@pytest.fixture(scope="module")
+def engines(clip_sd):
+    dev = torch.device("cuda")
+    return VisionEngine(clip_sd, dev), TextEngine(clip_sd, dev)
+
+
+def test_forward_matches_reference_golden(engines, golden_model):
+    vision, text = engines
+    g = golden_model
+    images = S.make_images(g["meta"]["B"], 0).cuda()
+    tokens = g["tokens"].cuda()
+    fac = {k: v.cuda() for k, v in S.make_prompt_factors(0).items()}
+    vis, txt = lpi_step.reconstruct(fac)
+    assert torch.allclose(vis[0].cpu(), g["prompt0"]["vis_l0"], atol=1e-6)
+    img_f, _ = vision.forward(images, vis.unsqueeze(0))
+    txt_f, _ = text.forward(tokens, txt.unsqueeze(0))
+    want = g["step_task1"]
+    assert _rel(img_f, want["img_f"]) < 1e-2 and _rel(txt_f, want["txt_f"]) < 1e-2
+    # un-prompted paths (extract_vector / extract_textual_vector, slinet.py:94-107)
+    f0, _ = vision.forward(images, None)
+    t0, _ = text.forward(tokens, None)
+    assert _rel(f0, g["extract_vector"]) < 1e-2 and _rel(t0, g["extract_textual_vector"]) < 1e-2
+    # per-sample prompt selection (visual_interface / textual_interface, slinet.py:185-220)
+    cat = g["interface_cat"]
+    tabs = [lpi_step.reconstruct({k: v.cuda() for k, v in S.make_prompt_factors(s).items()}) for s in (0, 1)]
+    vt = torch.stack([t[0] for t in tabs])
+    tt = torch.stack([t[1] for t in tabs])
+    sel = torch.as_tensor(cat, dtype=torch.int32).cuda()
+    fi, _ = vision.forward(images, vt, sel)
+    ti, _ = text.forward(tokens, tt, sel)
+    assert _rel(fi, g["visual_interface"]) < 1e-2 and _rel(ti, g["textual_interface"]) < 1e-2
+
+
+@pytest.mark.parametrize("task", [1, 2])
+def test_train_step_matches_reference_golden(engines, golden_model, task):
+    vision, text = engines
+    g = golden_model
+    images = S.make_images(g["meta"]["B"], 0).cuda()
+    tokens = g["tokens"].cuda()
+    scale = float(np.exp(np.log(1 / 0.07)))
+    if task == 1:
+        fac = {k: v.cuda() for k, v in S.make_prompt_factors(0).items()}
+        r = lpi_step.train_step(vision, text, fac, images, tokens, scale)
+        want = g["step_task1"]
+    else:
+        fac = {k: v.cuda() for k, v in S.make_prompt_factors(1).items()}
+        prev = [lpi_step.reconstruct({k: v.cuda() for k, v in S.make_prompt_factors(0).items()})]
+        sim = np.loadtxt(os.path.join(os.path.dirname(os.path.abspath(ops.__file__)), "MID", "task_sim_matrix.txt"))
+        tgt = torch.tensor((sim[:2, :2] > 0.4).astype(np.int32)).cuda()
+        r = lpi_step.train_step(vision, text, fac, images, tokens, scale, prev, tgt)
+        want = g["step_task2"]
+    assert set(r["losses"]) == set(want["losses"])
+    for k, v in want["losses"].items():
+        assert abs(float(r["losses"][k]) - v) < 1e-2 * max(abs(v), 1e-3), (k, float(r["losses"][k]), v)
+    for k in O.FACTOR_NAMES:
+        assert _rel(r["grads"][k], want["grads"][k]) < 2e-2, (k, _rel(r["grads"][k], want["grads"][k]))
+
+
+def test_train_step_vs_oracle_fresh_inputs(engines, clip_sd):
+    """A second, independent input set (not in the fixtures): CUDA step vs the CPU oracle restatement, B = 3,
+    including the opt-in depth-3 injection mode (inject_layers = {1, 2})."""
+    vision, text = engines
+    images, tokens = S.make_images(3, 7), S.make_tokens(3, 7)
+    facs = S.make_prompt_factors(4)
+    for inject in ((), (1, 2)):
+        want = O.train_step(clip_sd, facs, images, tokens, inject_layers=inject)
+        r = lpi_step.train_step(vision, text, {k: v.cuda() for k, v in facs.items()}, images.cuda(), tokens.cuda(), 1 / 0.07,
+                                inject_layers=inject)
+        assert _rel(r["img_f"], want["img_f"]) < 1e-2 and _rel(r["txt_f"], want["txt_f"]) < 1e-2
+        for k, v in want["losses"].items():
+            assert abs(float(r["losses"][k]) - v) < 1e-2 * max(abs(v), 1e-3), (inject, k)
+        for k in O.FACTOR_NAMES:
+            assert _rel(r["grads"][k], want["grads"][k]) < 2e-2, (inject, k, _rel(r["grads"][k], want["grads"][k]))
