@@ -224,6 +224,7 @@ class TextEngine:
         self.width = self.emb.shape[1]
         self.tower = Tower(sd, "transformer.resblocks.", self.width // 64, True, dev, need_grad)
         self.context_length = self.pos.shape[0]
+        self.zero_pos = torch.zeros_like(self.pos)
         self.dev = dev
 
     def forward(self, tokens: torch.Tensor, prompt_table: Optional[torch.Tensor] = None, sel: Optional[torch.Tensor] = None,
@@ -262,3 +263,38 @@ class TextEngine:
         for l, gl in inj_grads.items():
             G[:, l] = gl
         return G
+
+    # ---- the reference's module boundary: TextEncoder.forward(prompts [B,77,D] already embedded + spliced, tokenized, ...)
+    def forward_embedded(self, prompts: torch.Tensor, tokens: torch.Tensor, prompt_table: Optional[torch.Tensor] = None,
+                         sel: Optional[torch.Tensor] = None, tape: Optional[dict] = None, inject_layers: Sequence[int] = ()):
+        B, L, D = prompts.shape
+        rows_all = torch.arange(B * L, device=prompts.device, dtype=torch.int64)
+        x = ops.assemble_text(prompts.reshape(B * L, D), rows_all.view(B, L), self.pos, None, None, B, L, 0, D)    # + positional_embedding
+        inject = None
+        if prompt_table is not None and len(inject_layers) > 0:
+            inject = {"layers": set(int(l) for l in inject_layers), "table": prompt_table, "sel": sel, "P": prompt_table.shape[2]}
+        ttape = TowerTape(B, L) if tape is not None else None
+        x = self.tower.forward(x, B, L, ttape, inject)
+        rows = (torch.arange(B, device=x.device, dtype=torch.int64) * L + tokens.argmax(dim=-1)).to(torch.int32)
+        feat, z = ops.head_fwd(x, rows, self.ln_final[0], self.ln_final[1], self.proj)
+        if tape is not None:
+            tape.update(dict(tower=ttape, rows=rows, z=z, x=x, sel=sel, L=L, B=B, inject=inject,
+                             table_shape=None if prompt_table is None else tuple(prompt_table.shape)))
+        return feat, z
+
+    def backward_embedded(self, tape: dict, dfeat: Optional[torch.Tensor], dz: Optional[torch.Tensor] = None):
+        """-> (d loss / d prompts [B*L, D], d loss / d prompt_table or None)"""
+        B, L, D = tape["B"], tape["L"], self.width
+        dev = tape["x"].device
+        g = torch.zeros(B * L, D, device=dev, dtype=torch.float32)
+        gb = torch.zeros(B * L, D, device=dev, dtype=torch.bfloat16)
+        ops.head_bwd(None if dfeat is None else dfeat.contiguous(), None if dz is None else dz.contiguous(), tape["z"], tape["x"],
+                     tape["rows"], self.ln_final[0], self.proj, g, gb)
+        inj_grads = {}
+        self.tower.backward(tape["tower"], g, gb, tape["inject"], inj_grads)
+        G = None
+        if tape["table_shape"] is not None:
+            G = torch.zeros(tape["table_shape"], device=dev, dtype=torch.float32)
+            for l, gl in inj_grads.items():
+                G[:, l] = gl
+        return g, G

@@ -1,0 +1,302 @@
+"""SPrompts -- the LPI learner with the reference's surface (retrieval/methods/sprompt.py:104-646 + the BaseLearner fields
+it uses, retrieval/methods/base.py:14-28): incremental_train / after_task / _train / train_function / clustering /
+get_visual_task_id / get_textual_task_id / _evaluate_retrieval / itm_eval, plus gather_features (sprompt.py:38-82).
+
+What runs where: encoders, losses, backward, SGD step, task-id selection, similarity + top-k + Recall@K are CUDA kernels
+(liblpi_b200.so); K-Means for the task keys stays on the host with sklearn (random_state=0) for parity; data
+loading is the caller's business -- pass loaders (any Dataset yielding the reference's item tuples) instead of COCO paths.
+Multi-GPU: one process per GPU; pass a torch.distributed group via args['group'] -- the batch is sharded, features are
+all-gathered once, the 21 KB prompt gradient is all-reduced once (the reference only supports a single GPU, README.md:13).
+"""
+from __future__ import annotations
+
+import collections
+import json
+import logging
+import os
+from datetime import datetime
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+from torch import nn, optim
+
+from . import lpi_step, ops, retrieval
+from ._lib import LpiError
+from .loss import ClipLoss
+from .slinet import SliNet, load_task_sim_matrix
+from . import losses as L
+
+
+def gather_features(image_features, text_features, local_loss=False, gather_with_grad=False, rank=0, world_size=1, use_horovod=False):
+    """sprompt.py:38-82 (open_clip style): all-gather both feature sets; without gather_with_grad the local slot keeps its own
+    (grad-carrying) tensors.  Dead code in the reference (never called); here it is the documented DP entry point."""
+    import torch.distributed as dist
+
+    if use_horovod:
+        raise LpiError("horovod is not supported; use torch.distributed (NCCL)")
+    if world_size == 1:
+        return image_features, text_features
+    if gather_with_grad:
+        import torch.distributed.nn
+
+        all_image_features = torch.cat(torch.distributed.nn.all_gather(image_features), dim=0)
+        all_text_features = torch.cat(torch.distributed.nn.all_gather(text_features), dim=0)
+    else:
+        gi = [torch.zeros_like(image_features) for _ in range(world_size)]
+        gt = [torch.zeros_like(text_features) for _ in range(world_size)]
+        dist.all_gather(gi, image_features)
+        dist.all_gather(gt, text_features)
+        if not local_loss:
+            gi[rank] = image_features
+            gt[rank] = text_features
+        all_image_features = torch.cat(gi, dim=0)
+        all_text_features = torch.cat(gt, dim=0)
+    return all_image_features, all_text_features
+
+
+class AverageMeter(object):
+    def __init__(self):
+        self.reset()
+
+    def reset(self):
+        self.val = self.avg = self.sum = self.count = 0
+
+    def update(self, val, n=1):
+        self.val = val
+        self.sum += val * n
+        self.count += n
+        self.avg = self.sum / self.count
+
+
+class FusedSGD(optim.Optimizer):
+    """torch.optim.SGD(momentum, weight_decay) semantics (no dampening / nesterov, sprompt.py:253) as one kernel per tensor.
+    Parameters without a gradient are skipped, exactly like torch (the reference hands SGD all 149.8 M parameters of which
+    5 284 ever receive a gradient)."""
+
+    def __init__(self, params, lr, momentum=0.9, weight_decay=0.0):
+        super().__init__(params, dict(lr=lr, momentum=momentum, weight_decay=weight_decay))
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        for group in self.param_groups:
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                st = self.state[p]
+                first = "momentum_buffer" not in st
+                if first:
+                    st["momentum_buffer"] = torch.zeros_like(p)
+                ops.sgd_momentum_step(p.data, p.grad.contiguous(), st["momentum_buffer"], group["lr"], group["momentum"],
+                                      group["weight_decay"], first)
+
+
+class SPrompts(object):
+    def __init__(self, args):
+        # BaseLearner fields (base.py:14-28)
+        self._cur_task = -1
+        self._known_classes = 0
+        self._total_classes = 0
+        self._old_network = None
+        self._device = args["device"][0] if isinstance(args["device"], (list, tuple)) else args["device"]
+        self._multiple_gpus = args["device"] if isinstance(args["device"], (list, tuple)) else [args["device"]]
+        if args["net_type"] != "slip":
+            raise ValueError("Unknown net: {}.".format(args["net_type"]))
+        self._network = SliNet(args)
+        self.args = args
+        self.EPSILON = args["EPSILON"]
+        self.init_epoch, self.init_lr = args["init_epoch"], args["init_lr"]
+        self.init_lr_decay, self.init_weight_decay = args["init_lr_decay"], args["init_weight_decay"]
+        self.epochs, self.lrate, self.lrate_decay = args["epochs"], args["lrate"], args["lrate_decay"]
+        self.batch_size, self.weight_decay, self.num_workers = args["batch_size"], args["weight_decay"], args["num_workers"]
+        self.topk = 2
+        self.class_num = self._network.class_num
+        self.all_keys: List[torch.Tensor] = []
+        self.textual_all_keys: List[torch.Tensor] = []
+        self.loss = ClipLoss()
+        self.cur_id = 0
+        self.group = args.get("group")                    # torch.distributed process group for data-parallel training
+        self.fused_step = bool(args.get("fused_step", True))
+        self.n_tasks = int(args.get("n_tasks", args["total_sessions"]))
+        self.log = logging.getLogger("lpi_b200")
+
+    # ------------------------------------------------------------------ task loop
+    def after_task(self):
+        """sprompt.py:145-148 deep-copies the whole 149.8 M-parameter network and never uses it; only the
+        bookkeeping is kept."""
+        self._known_classes = self._total_classes
+
+    def incremental_train(self, task_loaders: Optional[Sequence] = None):
+        """sprompt.py:150-187.  task_loaders[i] = (train_loader, test_loader) for task i; the test loader covers tasks 0..i.
+        Returns {task: result dict} and writes ./res/<datetime>.json like the reference."""
+        task_loaders = task_loaders if task_loaders is not None else self.args.get("task_loaders")
+        if task_loaders is None:
+            raise LpiError("pass task_loaders=[(train_loader, test_loader), ...]: the COCO file datasets of the reference "
+                           "(utils/data.py) are outside the hot path (SURVEY.md section 8(f) f4)")
+        final_res = {}
+        for i in range(min(self.n_tasks, len(task_loaders))):
+            self._cur_task = [i]
+            self.cur_id = i
+            self._network.update_fc(self._total_classes)
+            self.train_loader, self.test_loader = task_loaders[i]
+            final_res[i] = self._train(self.train_loader, self.test_loader)
+        os.makedirs("./res", exist_ok=True)
+        self.save_dict(final_res, f"./res/{datetime.now()}.json")
+        return final_res
+
+    def save_dict(self, dictionary, file_path):
+        with open(file_path, "w") as f:
+            json.dump(dictionary, f)
+
+    def _train(self, train_loader, test_loader):
+        self._network.to(self._device)
+        network = self._network
+        for name, param in network.named_parameters():          # freeze all but "prompts.{t}." (sprompt.py:229-237)
+            param.requires_grad_(False)
+            if "prompts" + "." + str(network.numtask - 1) + "." in name:
+                param.requires_grad_(True)
+        optimizer = FusedSGD(self._network.parameters(), momentum=0.9, lr=self.lrate, weight_decay=self.weight_decay)
+        scheduler = optim.lr_scheduler.CosineAnnealingLR(optimizer=optimizer, T_max=self.epochs)
+        self.run_epoch = self.epochs
+        return self.train_function(train_loader, test_loader, optimizer, scheduler)
+
+    # ------------------------------------------------------------------ hot loop
+    def _step_autograd(self, images, captions, optimizer):
+        image_features, text_features, visual_prompt, textual_prompt = self._network(images, captions)
+        model_out = self._network.cal_loss(image_features, text_features, visual_prompt, textual_prompt)
+        loss = sum(l for l in model_out["loss"].values())
+        optimizer.zero_grad()
+        loss.backward()
+        optimizer.step()
+        return model_out["loss"]
+
+    def _step_fused(self, images, captions, optimizer):
+        """Same maths as _step_autograd without the autograd graph; supports the data-parallel group."""
+        net = self._network
+        t = net.numtask - 1
+        prompt = net.prompts[t]
+        factors = {k: getattr(prompt, k).data for k in lpi_step.FACTOR_NAMES}
+        tokens = captions if isinstance(captions, torch.Tensor) else net.classifier_pool[t].tokenize(captions)
+        prev, target = [], None
+        if net.numtask != 1:
+            with torch.no_grad():
+                prev = [net.prompts[i]() for i in range(t)]
+            sim = load_task_sim_matrix() if net._task_sim is None else net._task_sim
+            net._task_sim = sim
+            target = torch.tensor((sim[:t + 1, :t + 1] > L.TASK_THRESHOLD).astype(np.int32), device=images.device)
+        r = lpi_step.train_step(net.image_encoder.engine(), net.clip_model.text_engine(), factors, images.float(), tokens,
+                                float(net.logit_scale.exp()), prev, target, tuple(net.clip_model.inject_layers), self.group)
+        optimizer.zero_grad()
+        for k in lpi_step.FACTOR_NAMES:
+            getattr(prompt, k).grad = r["grads"][k]
+        optimizer.step()
+        return {k: v.view(()) for k, v in r["losses"].items()}
+
+    def train_function(self, train_loader, test_loader, optimizer, scheduler):
+        """sprompt.py:290-334"""
+        loss_meter = collections.defaultdict(AverageMeter)
+        for epoch in range(self.run_epoch):
+            self._network.train()
+            for i, (images, captions, _, _) in enumerate(train_loader):
+                images = images.to(self._device, non_blocking=True)
+                captions = captions if isinstance(captions, torch.Tensor) else list(captions)
+                if isinstance(captions, torch.Tensor):
+                    captions = captions.to(self._device, non_blocking=True)
+                step = self._step_fused if (self.fused_step or self.group is not None) else self._step_autograd
+                out = step(images, captions, optimizer)
+                for k, v in out.items():
+                    loss_meter[k].update(v.detach())              # stays on the device: no per-step sync
+                if i % 50 == 0:
+                    info = "Task {}, Epoch {}/{}, Batch {}, lr {:.4f} =>, ".format(self.cur_id, epoch + 1, self.run_epoch, i,
+                                                                                   optimizer.param_groups[0]["lr"])
+                    for k, v in loss_meter.items():
+                        info += "{} = {:.4f}, ".format(k, float(v.avg))
+                        v.reset()
+                    self.log.info(info)
+            scheduler.step()
+        self.clustering(dataloader=train_loader)
+        _, _, final_res = self._evaluate_retrieval(test_loader)
+        return final_res
+
+    # ------------------------------------------------------------------ task keys / task-id
+    def _task_id(self, feature, keys):
+        return ops.nearest_center_l1(feature.float().contiguous(), torch.stack([k.float() for k in keys]).contiguous())
+
+    def get_visual_task_id(self, inputs):
+        """sprompt.py:336-351: argmin over tasks of the min L1 distance to the task's 5 centres."""
+        with torch.no_grad():
+            return self._task_id(self._network.extract_vector(inputs), self.all_keys)
+
+    def get_textual_task_id(self, inputs):
+        with torch.no_grad():
+            return self._task_id(self._network.extract_textual_vector(inputs), self.textual_all_keys)
+
+    def clustering(self, dataloader):
+        """sprompt.py:370-397: un-prompted features of the task's train set -> KMeans(5, random_state=0) centres (host, sklearn)."""
+        from sklearn.cluster import KMeans
+
+        vf, tf = [], []
+        with torch.no_grad():
+            for inputs, captions, _, _ in dataloader:
+                inputs = inputs.to(self._device)
+                captions = captions.to(self._device) if isinstance(captions, torch.Tensor) else list(captions)
+                vf.append(self._network.extract_vector(inputs))
+                tf.append(self._network.extract_textual_vector(captions))
+        vf = torch.cat(vf, 0)
+        tf = torch.cat(tf, 0)
+        vf = ops.l2_normalize(vf.contiguous()).cpu().numpy()       # the reference re-normalises (sprompt.py:387-390)
+        tf = ops.l2_normalize(tf.contiguous()).cpu().numpy()
+        vc = KMeans(n_clusters=5, random_state=0).fit(vf)
+        tc = KMeans(n_clusters=5, random_state=0).fit(tf)
+        self.all_keys.append(torch.tensor(vc.cluster_centers_).to(self._device))
+        self.textual_all_keys.append(torch.tensor(tc.cluster_centers_).to(self._device))
+
+    # ------------------------------------------------------------------ evaluation
+    @torch.no_grad()
+    def _evaluate_retrieval(self, data_loader, return_scores: Optional[bool] = None):
+        """sprompt.py:433-548 -> (score_matrix_i2t, score_matrix_t2i, final_res).  The dense matrices are only materialised
+        (numpy, like the reference) when small (<= 5e7 entries) or when return_scores=True; Recall@K itself never needs them."""
+        self._network.eval()
+        ds = data_loader.dataset
+        texts = ds.text
+        texts_cat = torch.as_tensor(ds.text_cat)
+        image_feats, category_i = [], []
+        for image, img_id, category in data_loader:
+            image = image.to(self._device)
+            if self.args["prompt_type"] == "clip":
+                feat = self._network.extract_vector(image)
+            else:
+                selection = self.get_visual_task_id(image)
+                feat = self._network.visual_interface(image, selection)
+            image_feats.append(feat)
+            category_i.extend(int(z) for z in category)
+        image_feats = torch.cat(image_feats)
+        text_feats = []
+        text_bs = 256
+        num_text = len(texts)
+        for i in range(0, num_text, text_bs):
+            text = texts[i:min(num_text, i + text_bs)]
+            if isinstance(text, torch.Tensor):
+                text = text.to(self._device)
+            if self.args["prompt_type"] == "clip":
+                tfeat = self._network.extract_textual_vector(text)
+            else:
+                tsel = self.get_textual_task_id(text)
+                tfeat = self._network.textual_interface(text, tsel)
+            text_feats.append(tfeat)
+        text_feats = torch.cat(text_feats)
+        final_res = retrieval.itm_eval_features(image_feats, text_feats, ds.txt2img, ds.img2txt, category_i, texts_cat.tolist(),
+                                                self.cur_id + 1, precision="fp32")
+        n = image_feats.shape[0] * text_feats.shape[0]
+        if return_scores is None:
+            return_scores = n <= 50_000_000
+        if return_scores:
+            s = ops.sgemm(image_feats, text_feats.t())
+            s_i2t = s.cpu().numpy()
+            return s_i2t, np.ascontiguousarray(s_i2t.T), final_res
+        return None, None, final_res
+
+    @torch.no_grad()
+    def itm_eval(self, scores_i2t, scores_t2i, txt2img, img2txt, category_i, category_t):
+        """sprompt.py:550-646 on dense score matrices (drop-in signature)."""
+        return retrieval.itm_eval(scores_i2t, scores_t2i, txt2img, img2txt, category_i, category_t, self.cur_id + 1, device=self._device)

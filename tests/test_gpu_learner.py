@@ -1,0 +1,126 @@
+"""-m gpu parity of the nn.Module / learner surface (slinet.py, sprompt.py) against fixtures produced by the REAL reference:
+model_b4_seed0.pt (SliNet.forward / cal_loss / backward, the interfaces) and learner_2task_seed0.pt (the whole SPrompts learner on
+two synthetic tasks: SGD steps, K-Means keys, task-id selection, evaluation)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from lpi_b200 import data as D, synthetic as S
+from lpi_b200.config import default_args
+from lpi_b200.slinet import SliNet
+from lpi_b200.sprompt import SPrompts
+from oracle import lpi_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _rel(a, b):
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / b.norm())
+
+
+def _net(clip_sd, n_prompt_tasks=2, **kw):
+    args = default_args(clip_state_dict=clip_sd, device=[torch.device("cuda")], **kw)
+    net = SliNet(args)
+    with torch.no_grad():
+        for t in range(n_prompt_tasks):
+            for k, v in S.make_prompt_factors(t).items():
+                getattr(net.prompts[t], k).copy_(v)
+    return net.cuda(), args
+
+
+def test_slinet_autograd_path_matches_reference(clip_sd, golden_model):
+    g = golden_model
+    net, _ = _net(clip_sd)
+    net.update_fc(0)
+    images = S.make_images(g["meta"]["B"], 0).cuda()
+    captions = g["captions"]
+    for numtask, key in ((1, "step_task1"), (2, "step_task2")):
+        net.numtask = numtask
+        net.train()
+        for n, p in net.named_parameters():
+            p.requires_grad_(f"prompts.{numtask - 1}." in n)
+            p.grad = None
+        img_f, txt_f, vp, tp = net(images, captions)
+        assert vp.shape == (4, 9, 16, 768) and tp.shape == (4, 9, 16, 512)
+        out = net.cal_loss(img_f, txt_f, vp, tp)
+        sum(out["loss"].values()).backward()
+        want = g[key]
+        assert _rel(img_f, want["img_f"]) < 1e-2 and _rel(txt_f, want["txt_f"]) < 1e-2
+        assert set(out["loss"]) == set(want["losses"])
+        for k, v in want["losses"].items():
+            assert abs(float(out["loss"][k]) - v) < 1e-2 * max(abs(v), 1e-3), k
+        for k in O.FACTOR_NAMES:
+            got = getattr(net.prompts[numtask - 1], k).grad
+            assert _rel(got, want["grads"][k]) < 2e-2, (key, k, _rel(got, want["grads"][k]))
+        frozen = [n for n, p in net.named_parameters() if p.grad is not None and f"prompts.{numtask - 1}." not in n]
+        assert not frozen
+    # evaluation interfaces with string captions (tokeniser + per-sample task prompts)
+    net.eval()
+    net.numtask = 1
+    with torch.no_grad():
+        assert _rel(net.extract_vector(images), g["extract_vector"]) < 1e-2
+        assert _rel(net.extract_textual_vector(captions), g["extract_textual_vector"]) < 1e-2
+        net.numtask = 2
+        assert _rel(net.visual_interface(images, g["interface_cat"]), g["visual_interface"]) < 1e-2
+        assert _rel(net.textual_interface(captions, g["interface_cat"]), g["textual_interface"]) < 1e-2
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_learner_two_tasks_matches_reference(clip_sd, fused, tmp_path, monkeypatch):
+    monkeypatch.chdir(tmp_path)
+    g = torch.load(os.path.join(GOLDEN, "learner_2task_seed0.pt"), weights_only=False)
+    cfg = g["cfg"]
+    args = default_args(clip_state_dict=clip_sd, device=[torch.device("cuda")], epochs=cfg["epochs"], batch_size=cfg["batch_size"],
+                        fused_step=fused, n_tasks=cfg["n_tasks"])
+    learner = SPrompts(args)
+    net = learner._network
+    with torch.no_grad():
+        for t in range(cfg["n_tasks"]):
+            for k, v in S.make_prompt_factors(t).items():
+                getattr(net.prompts[t], k).copy_(v)
+    loaders = D.make_task_loaders(cfg["n_tasks"], cfg["n_train"], cfg["n_eval_images"], cfg["caps_per_image"], cfg["batch_size"],
+                                  cfg["eval_batch_size"])
+    logged = []
+    step_name = "_step_fused" if fused else "_step_autograd"
+    orig = getattr(learner, step_name)
+
+    def spy(*a, **k):
+        out = orig(*a, **k)
+        logged.append({n: float(v) for n, v in out.items()})
+        return out
+
+    setattr(learner, step_name, spy)
+    for t in range(cfg["n_tasks"]):
+        learner.cur_id = t
+        net.update_fc(0)
+        logged.clear()
+        res = learner._train(*loaders[t])
+        want = g["tasks"][t]
+        assert len(logged) == len(want["losses"])
+        for got_l, want_l in zip(logged, want["losses"]):
+            assert set(got_l) == set(want_l)
+            for k, v in want_l.items():
+                assert abs(got_l[k] - v) < 1e-2 * max(abs(v), 1e-3), (t, k, got_l[k], v)
+        for k in O.FACTOR_NAMES:                                  # parameters after the SGD steps of this task
+            assert _rel(getattr(net.prompts[t], k), want["factors"][k]) < 2e-3, (t, k)
+        assert _rel(learner.all_keys[t], want["keys_visual"]) < 2e-2 and _rel(learner.textual_all_keys[t], want["keys_textual"]) < 2e-2
+        ds = loaders[t][1].dataset
+        with torch.no_grad():
+            imgs = torch.stack(ds.image).cuda()
+            sel_i = learner.get_visual_task_id(imgs)
+            sel_t = learner.get_textual_task_id(ds.text)
+            f_i = net.visual_interface(imgs, want["sel_i"].cuda())
+            f_t = net.textual_interface(ds.text, want["sel_t"].cuda())
+        assert (sel_i.cpu() == want["sel_i"]).float().mean() >= 0.9 and (sel_t.cpu() == want["sel_t"]).float().mean() >= 0.9
+        assert _rel(f_i, want["img_f"]) < 1e-2 and _rel(f_t, want["txt_f"]) < 1.5e-2
+        # result dict: same schema as the reference, and bit-exact w.r.t. the oracle's itm_eval on the SAME features
+        assert set(res["mscoco"]) == {"i2t", "t2i"} and set(res["mscoco"]["i2t"]) == set(range(t + 1))
+        s_i2t, s_t2i, res2 = learner._evaluate_retrieval(loaders[t][1])
+        assert res2 == res
+        cat_i = [int(c) for c in ds.cat]
+        assert O.itm_eval(s_i2t, s_t2i, ds.txt2img, ds.img2txt, cat_i, ds.text_cat, t + 1) == res
+        assert learner.itm_eval(s_i2t, s_t2i, ds.txt2img, ds.img2txt, cat_i, np.asarray(ds.text_cat)) == res
