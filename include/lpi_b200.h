@@ -44,11 +44,18 @@ enum lpi_epilogue {
     EPI_ACC_F32 = 4,        /* out(fp32) += acc; out2(bf16, optional) = same             (dgrad into a stream)  */
     EPI_DGELU_BF16 = 5,     /* out(bf16)  = acc * QuickGELU'(aux)                        (c_proj dgrad)         */
     EPI_BF16 = 6,           /* out(bf16)  = acc                                          (out_proj dgrad)       */
-    EPI_BIAS_F32 = 7        /* out(fp32)  = acc + bias                                   (patch embedding)      */
+    EPI_BIAS_F32 = 7,       /* out(fp32)  = acc + bias                                   (patch embedding)      */
+    EPI_BIAS_GELU_F32 = 8,  /* out(fp32)  = QuickGELU(acc + bias); out2(fp32) = acc+bias  (c_fc, TF32 towers only)  */
+    EPI_DGELU_F32 = 9       /* out(fp32)  = acc * QuickGELU'(aux fp32)                    (c_proj dgrad, TF32 only)  */
 };
 int lpi_gemm_bf16(const void* A, const void* B, int M, int N, int K, int epi, const void* bias_f32,
                   const void* resid_f32, void* out, void* out2, const void* aux_bf16, int ldo, int tile_n,
                   void* stream);
+/* Same pipeline with fp32 operands in memory and tcgen05.mma kind::tf32 (10-bit mantissa, half the bf16 rate): the text tower
+ * runs on it because its gradients sit at the 2e-2 parity limit with bf16 operands (SURVEY.md section 7 error budget).
+ * A [M,K] fp32, B [N,K] fp32, K % 32 == 0.  Epilogues: BIAS_BF16, BIAS_RESID_F32, F32, BF16, BIAS_GELU_F32, DGELU_F32. */
+int lpi_gemm_tf32(const void* A, const void* B, int M, int N, int K, int epi, const void* bias_f32, const void* resid_f32,
+                  void* out, void* out2, const void* aux, int ldo, int tile_n, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Retrieval scorer: similarity GEMM with the top-k kept in the epilogue (score matrix never written).
@@ -90,9 +97,11 @@ int lpi_l2_normalize(const float* x, int n, int dim, float* out, float* norm_out
  * qkv [B*L, 3*H*64] bf16 (row = b*L + l; columns q | k | v), out / d_out [B*L, H*64] bf16, lse2 [B*H*L] fp32
  * (log2-domain log-sum-exp saved by the forward for the backward), delta_ws [B*H*L] fp32 scratch, dqkv like qkv.
  * ------------------------------------------------------------------------------------------------ */
-int lpi_attn_fwd(const void* qkv, void* out, float* lse2, int B, int L, int H, int causal, void* stream);
+int lpi_attn_fwd(const void* qkv, void* out, float* out_f32 /* optional fp32 copy of out */, float* lse2, int B, int L, int H,
+                 int causal, void* stream);
 int lpi_attn_bwd(const void* qkv, const void* out, const void* d_out, const float* lse2, float* delta_ws, void* dqkv,
-                 int B, int L, int H, int causal, void* stream);
+                 float* dqkv_f32 /* if non-NULL the gradient is written here in fp32 instead of dqkv */, int B, int L, int H,
+                 int causal, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * LayerNorm in fp32 (models/clip/model.py:154-160; eps inside the sqrt, biased variance).

@@ -119,6 +119,7 @@ class CLIP(nn.Module):
         self.text_projection = nn.Parameter(torch.empty(transformer_width, embed_dim))
         self.logit_scale = nn.Parameter(torch.ones([]) * np.log(1 / 0.07))
         self.inject_layers: Tuple[int, ...] = ()
+        self.text_precision = "tf32"          # 'tf32' (parity default) or 'bf16' -- see engine.TextEngine
         self._text_engine: Optional[TextEngine] = None
         self.initialize_parameters()
 
@@ -152,7 +153,7 @@ class CLIP(nn.Module):
             raise LpiError("lpi_b200 runs on a CUDA (sm_100a) device only; move the model with .cuda() first")
         if self._text_engine is None or self._text_engine.dev != dev:
             sd = {k: v for k, v in self.state_dict().items() if not k.startswith("visual.")}
-            self._text_engine = TextEngine(sd, dev)
+            self._text_engine = TextEngine(sd, dev, precision=self.text_precision)
         return self._text_engine
 
     def refresh(self):

@@ -125,11 +125,25 @@ __device__ __forceinline__ void store_tile_bf16(const float (&c)[8][4], __nv_bfl
     }
 }
 
+// same tile as fp32 rows (TF32 consumers: the text tower's out_proj / in_proj dgrad GEMMs read fp32 operands)
+__device__ __forceinline__ void store_tile_f32(const float (&c)[8][4], float* base, long ld, int row0, int L, float mul) {
+    const int lane = threadIdx.x & 31;
+    const int r = lane >> 2, cq = (lane & 3) * 2;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int row = row0 + r + h * 8;
+        if (row >= L) continue;
+        float* p = base + long(row) * ld + cq;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) *reinterpret_cast<float2*>(p + nt * 8) = make_float2(c[nt][2 * h] * mul, c[nt][2 * h + 1] * mul);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ forward
 template <bool CAUSAL>
 __global__ void __launch_bounds__(ATT_THREADS)
-attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, float* __restrict__ lse2,
-                int L, int H, float scale_log2) {
+attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, float* __restrict__ out_f32,
+                float* __restrict__ lse2, int L, int H, float scale_log2) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int qc = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int D = H * DH;
@@ -200,6 +214,7 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) { o[nt][0] *= inv0; o[nt][1] *= inv0; o[nt][2] *= inv1; o[nt][3] *= inv1; }
     store_tile_bf16(o, out + long(b) * L * D + h * DH, D, q0 + warp * 16, L, 1.f);
+    if (out_f32) store_tile_f32(o, out_f32 + long(b) * L * D + h * DH, D, q0 + warp * 16, L, 1.f);
     if (lse2 && (lane & 3) == 0) {
         float* lp = lse2 + (long(b) * H + h) * L;
         if (r_lo < L) lp[r_lo] = m[0] + log2f(l[0]);
@@ -228,7 +243,8 @@ __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __n
 template <bool CAUSAL>
 __global__ void __launch_bounds__(ATT_THREADS)
 attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ d_o, const float* __restrict__ lse2,
-                   const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int L, int H, float scale, float scale_log2) {
+                   const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dqkv_f32, int L, int H, float scale,
+                   float scale_log2) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int qc = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int D = H * DH;
@@ -286,14 +302,16 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
         acc_to_a(s, dsa);
         mma_p_t(dq, dsa, sK, kb * 64);
     }
-    store_tile_bf16(dq, dqkv + long(b) * L * ld + h * DH, ld, q0 + warp * 16, L, scale);
+    if (dqkv_f32) store_tile_f32(dq, dqkv_f32 + long(b) * L * ld + h * DH, ld, q0 + warp * 16, L, scale);
+    else store_tile_bf16(dq, dqkv + long(b) * L * ld + h * DH, ld, q0 + warp * 16, L, scale);
 }
 
 // dK, dV: CTA = 64 key rows of one (b, h); everything is computed transposed so each warp owns 16 keys.
 template <bool CAUSAL>
 __global__ void __launch_bounds__(ATT_THREADS)
 attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ d_o, const float* __restrict__ lse2,
-                    const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, int L, int H, float scale, float scale_log2) {
+                    const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dqkv_f32, int L, int H, float scale,
+                    float scale_log2) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int kc = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
     const int D = H * DH;
@@ -307,7 +325,7 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
     const __nv_bfloat16* base = qkv + long(b) * L * ld + h * DH;
     load_head_rows(sK, base + D, ld, k0, QB, L);
     load_head_rows(sV, base + 2 * D, ld, k0, QB, L);
-    load_head_rows(sQ, base - long(q_begin) * 0 + long(q_begin) * ld, ld, 0, nqb * 64, L - q_begin);
+    load_head_rows(sQ, base + long(q_begin) * ld, ld, 0, nqb * 64, L - q_begin);
     load_head_rows(sdO, d_o + (long(b) * L + q_begin) * D + h * DH, D, 0, nqb * 64, L - q_begin);
     for (int i = threadIdx.x; i < nqb * 64; i += ATT_THREADS) {
         const int row = q_begin + i;
@@ -355,9 +373,15 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
         mma_p_t(dv, pa, sdO, qb * 64);          // dV += P^T dO
         mma_p_t(dk, dsa, sQ, qb * 64);          // dK += dS^T Q
     }
-    __nv_bfloat16* dbase = dqkv + long(b) * L * ld + h * DH;
-    store_tile_bf16(dk, dbase + D, ld, k0 + warp * 16, L, scale);
-    store_tile_bf16(dv, dbase + 2 * D, ld, k0 + warp * 16, L, 1.f);
+    if (dqkv_f32) {
+        float* dbase = dqkv_f32 + long(b) * L * ld + h * DH;
+        store_tile_f32(dk, dbase + D, ld, k0 + warp * 16, L, scale);
+        store_tile_f32(dv, dbase + 2 * D, ld, k0 + warp * 16, L, 1.f);
+    } else {
+        __nv_bfloat16* dbase = dqkv + long(b) * L * ld + h * DH;
+        store_tile_bf16(dk, dbase + D, ld, k0 + warp * 16, L, scale);
+        store_tile_bf16(dv, dbase + 2 * D, ld, k0 + warp * 16, L, 1.f);
+    }
 }
 
 static int attn_smem_fwd(int L) { return (QB + 2 * ((L + 63) / 64) * 64) * 128; }
@@ -382,7 +406,7 @@ static int attn_check(int B, int L, int H) {
     return 0;
 }
 
-extern "C" int lpi_attn_fwd(const void* qkv, void* out, float* lse2, int B, int L, int H, int causal, void* stream) {
+extern "C" int lpi_attn_fwd(const void* qkv, void* out, float* out_f32, float* lse2, int B, int L, int H, int causal, void* stream) {
     if (int rc = attn_check(B, L, H)) return rc;
     const float scale_log2 = 0.125f * 1.4426950408889634f;      // 1/sqrt(64) * log2(e)
     const dim3 grid((L + QB - 1) / QB, H, B);
@@ -392,17 +416,18 @@ extern "C" int lpi_attn_fwd(const void* qkv, void* out, float* lse2, int B, int 
     auto o = static_cast<__nv_bfloat16*>(out);
     if (causal) {
         if (int rc = set_smem(attn_fwd_kernel<true>, smem)) return rc;
-        attn_fwd_kernel<true><<<grid, ATT_THREADS, smem, st>>>(q, o, lse2, L, H, scale_log2);
+        attn_fwd_kernel<true><<<grid, ATT_THREADS, smem, st>>>(q, o, out_f32, lse2, L, H, scale_log2);
     } else {
         if (int rc = set_smem(attn_fwd_kernel<false>, smem)) return rc;
-        attn_fwd_kernel<false><<<grid, ATT_THREADS, smem, st>>>(q, o, lse2, L, H, scale_log2);
+        attn_fwd_kernel<false><<<grid, ATT_THREADS, smem, st>>>(q, o, out_f32, lse2, L, H, scale_log2);
     }
     return check_launch("attn_fwd");
 }
 
 extern "C" int lpi_attn_bwd(const void* qkv, const void* out, const void* d_out, const float* lse2, float* delta_ws, void* dqkv,
-                            int B, int L, int H, int causal, void* stream) {
+                            float* dqkv_f32, int B, int L, int H, int causal, void* stream) {
     if (int rc = attn_check(B, L, H)) return rc;
+    if (!dqkv && !dqkv_f32) return set_error(LPI_ERR_ARG, "attn_bwd: no output");
     const float scale = 0.125f, scale_log2 = 0.125f * 1.4426950408889634f;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     auto q = static_cast<const __nv_bfloat16*>(qkv);
@@ -415,13 +440,13 @@ extern "C" int lpi_attn_bwd(const void* qkv, const void* out, const void* d_out,
     if (causal) {
         if (int rc = set_smem(attn_bwd_dq_kernel<true>, attn_smem_dq(L))) return rc;
         if (int rc = set_smem(attn_bwd_dkv_kernel<true>, attn_smem_dkv(L))) return rc;
-        attn_bwd_dq_kernel<true><<<grid, ATT_THREADS, attn_smem_dq(L), st>>>(q, d_o, lse2, delta_ws, dq, L, H, scale, scale_log2);
-        attn_bwd_dkv_kernel<true><<<grid, ATT_THREADS, attn_smem_dkv(L), st>>>(q, d_o, lse2, delta_ws, dq, L, H, scale, scale_log2);
+        attn_bwd_dq_kernel<true><<<grid, ATT_THREADS, attn_smem_dq(L), st>>>(q, d_o, lse2, delta_ws, dq, dqkv_f32, L, H, scale, scale_log2);
+        attn_bwd_dkv_kernel<true><<<grid, ATT_THREADS, attn_smem_dkv(L), st>>>(q, d_o, lse2, delta_ws, dq, dqkv_f32, L, H, scale, scale_log2);
     } else {
         if (int rc = set_smem(attn_bwd_dq_kernel<false>, attn_smem_dq(L))) return rc;
         if (int rc = set_smem(attn_bwd_dkv_kernel<false>, attn_smem_dkv(L))) return rc;
-        attn_bwd_dq_kernel<false><<<grid, ATT_THREADS, attn_smem_dq(L), st>>>(q, d_o, lse2, delta_ws, dq, L, H, scale, scale_log2);
-        attn_bwd_dkv_kernel<false><<<grid, ATT_THREADS, attn_smem_dkv(L), st>>>(q, d_o, lse2, delta_ws, dq, L, H, scale, scale_log2);
+        attn_bwd_dq_kernel<false><<<grid, ATT_THREADS, attn_smem_dq(L), st>>>(q, d_o, lse2, delta_ws, dq, dqkv_f32, L, H, scale, scale_log2);
+        attn_bwd_dkv_kernel<false><<<grid, ATT_THREADS, attn_smem_dkv(L), st>>>(q, d_o, lse2, delta_ws, dq, dqkv_f32, L, H, scale, scale_log2);
     }
     return check_launch("attn_bwd");
 }

@@ -38,6 +38,8 @@ struct GemmArgs {
     __nv_bfloat16* out_bf16;       // [M, ldo]
     __nv_bfloat16* out2_bf16;      // [M, ldo] second output (pre-activation) or null
     const __nv_bfloat16* aux_bf16; // [M, ldo] (EPI_DGELU: saved pre-activation)
+    float* out2_f32;               // [M, ldo] fp32 pre-activation (EPI_BIAS_GELU_F32)
+    const float* aux_f32;          // [M, ldo] fp32 pre-activation (EPI_DGELU_F32)
     int ldo;
     // MODE_TOPK
     int k;                         // top-k (<= TOPK_MAX)
@@ -131,7 +133,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, const uint32_t
     float v[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-    if (EPI != EPI_F32 && EPI != EPI_ACC_F32 && EPI != EPI_DGELU_BF16 && EPI != EPI_BF16) {
+    if (EPI != EPI_F32 && EPI != EPI_ACC_F32 && EPI != EPI_DGELU_BF16 && EPI != EPI_BF16 && EPI != EPI_DGELU_F32) {
         const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -159,7 +161,25 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, const uint32_t
         }
         return;
     }
-    if (EPI == EPI_F32 || EPI == EPI_BIAS_F32) {
+    if (EPI == EPI_BIAS_GELU_F32) {       // fp32 activations for a TF32 consumer; fp32 pre-activation kept for the backward
+        if (p.out2_f32) {
+            float4* z4 = reinterpret_cast<float4*>(p.out2_f32 + off);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) z4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = quick_gelu(v[j]);
+    }
+    if (EPI == EPI_DGELU_F32) {
+        const float4* z4 = reinterpret_cast<const float4*>(p.aux_f32 + off);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 z = z4[j];
+            v[4 * j] *= quick_gelu_grad(z.x); v[4 * j + 1] *= quick_gelu_grad(z.y);
+            v[4 * j + 2] *= quick_gelu_grad(z.z); v[4 * j + 3] *= quick_gelu_grad(z.w);
+        }
+    }
+    if (EPI == EPI_F32 || EPI == EPI_BIAS_F32 || EPI == EPI_BIAS_GELU_F32 || EPI == EPI_DGELU_F32) {
         float4* d4 = reinterpret_cast<float4*>(p.out_f32 + off);
 #pragma unroll
         for (int j = 0; j < 8; ++j) d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -197,7 +217,8 @@ __device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, const uint32_t
                            pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
 }
 
-template <int MODE, int BN, int EPI>
+// TF32 = true: fp32 operands in memory (32 elements = 128 B per swizzle row), tcgen05.mma kind::tf32 (K = 8 per instruction)
+template <int MODE, int BN, int EPI, bool TF32 = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs p) {
     using C = Cfg<BN>;
@@ -213,7 +234,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int num_k = p.K / BK;
+    constexpr int BKE = TF32 ? 32 : BK;          // elements per 128-byte smem row
+    const int num_k = p.K / BKE;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -252,8 +274,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     mbar_wait(empty_bar(stage), phase ^ 1);
                     mbar_arrive_expect_tx(full_bar(stage), C::STAGE_BYTES);
                     const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
-                    tma_load_2d(sa, &tmA, full_bar(stage), kb * BK, m0);
-                    tma_load_2d(sa + A_STAGE_BYTES, &tmB, full_bar(stage), kb * BK, n0);
+                    tma_load_2d(sa, &tmA, full_bar(stage), kb * BKE, m0);
+                    tma_load_2d(sa + A_STAGE_BYTES, &tmB, full_bar(stage), kb * BKE, n0);
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -261,7 +283,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer (single thread)
         if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc(kFmtBF16, BM, BN, 0, 0);
+            constexpr uint32_t idesc = make_idesc(TF32 ? kFmtTF32 : kFmtBF16, BM, BN, 0, 0);
             TileWalk<MODE, BN> walk(p);
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0;
@@ -278,8 +300,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint64_t da = make_desc_kmajor_sw128(sa);
                     const uint64_t db = make_desc_kmajor_sw128(sa + A_STAGE_BYTES);
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k)   // +32 B per K step inside the 128 B swizzle row
-                        umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    for (int k = 0; k < BK / UMMA_K; ++k) { // +32 B per K step inside the 128 B swizzle row (16 bf16 or 8 tf32)
+                        if (TF32) umma_tf32_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        else umma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                    }
                     umma_commit(empty_bar(stage));           // smem slot reusable once these MMAs retire
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
@@ -414,9 +438,9 @@ int num_sms() {
     return g_num_sms;
 }
 
-template <int MODE, int BN, int EPI>
+template <int MODE, int BN, int EPI, bool TF32 = false>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, int grid, cudaStream_t st) {
-    auto kern = gemm_tn_kernel<MODE, BN, EPI>;
+    auto kern = gemm_tn_kernel<MODE, BN, EPI, TF32>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM_BYTES);
@@ -444,20 +468,36 @@ static int launch_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gemm
     return set_error(LPI_ERR_ARG, "unknown epilogue %d", a.epi);
 }
 
+template <int BN>
+static int launch_epi_tf32(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, int grid, cudaStream_t st) {
+    switch (a.epi) {
+        case EPI_BIAS_BF16: return launch<MODE_GEMM, BN, EPI_BIAS_BF16, true>(tmA, tmB, a, grid, st);
+        case EPI_BIAS_RESID_F32: return launch<MODE_GEMM, BN, EPI_BIAS_RESID_F32, true>(tmA, tmB, a, grid, st);
+        case EPI_F32: return launch<MODE_GEMM, BN, EPI_F32, true>(tmA, tmB, a, grid, st);
+        case EPI_BF16: return launch<MODE_GEMM, BN, EPI_BF16, true>(tmA, tmB, a, grid, st);
+        case EPI_BIAS_GELU_F32: return launch<MODE_GEMM, BN, EPI_BIAS_GELU_F32, true>(tmA, tmB, a, grid, st);
+        case EPI_DGELU_F32: return launch<MODE_GEMM, BN, EPI_DGELU_F32, true>(tmA, tmB, a, grid, st);
+    }
+    return set_error(LPI_ERR_ARG, "epilogue %d is not available for TF32 operands", a.epi);
+}
+
 }  // namespace lpi
 
 using namespace lpi;
 
-extern "C" int lpi_gemm_bf16(const void* A, const void* B, int M, int N, int K, int epi, const void* bias,
-                             const void* resid, void* out, void* out2, const void* aux, int ldo, int tile_n, void* stream) {
+static int gemm_entry(bool tf32, const void* A, const void* B, int M, int N, int K, int epi, const void* bias, const void* resid,
+                      void* out, void* out2, const void* aux, int ldo, int tile_n, void* stream) {
+    const int bke = tf32 ? 32 : BK;
     if (M <= 0 || N <= 0 || K <= 0) return set_error(LPI_ERR_ARG, "gemm: empty problem %dx%dx%d", M, N, K);
-    if (K % BK) return set_error(LPI_ERR_ARG, "gemm: K=%d must be a multiple of %d", K, BK);
+    if (K % bke) return set_error(LPI_ERR_ARG, "gemm: K=%d must be a multiple of %d", K, bke);
     if (N % 128) return set_error(LPI_ERR_ARG, "gemm: N=%d must be a multiple of 128", N);
     if (ldo < N || (ldo % 8)) return set_error(LPI_ERR_ARG, "gemm: bad ldo=%d", ldo);
-    const bool need_bias = (epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU_BF16 || epi == EPI_BIAS_RESID_F32 || epi == EPI_BIAS_F32);
+    const bool need_bias = (epi == EPI_BIAS_BF16 || epi == EPI_BIAS_GELU_BF16 || epi == EPI_BIAS_RESID_F32 || epi == EPI_BIAS_F32 ||
+                            epi == EPI_BIAS_GELU_F32);
     if (need_bias && !bias) return set_error(LPI_ERR_ARG, "gemm: epilogue %d needs a bias", epi);
     if (epi == EPI_BIAS_RESID_F32 && !resid) return set_error(LPI_ERR_ARG, "gemm: residual epilogue needs resid");
-    if (epi == EPI_DGELU_BF16 && !aux) return set_error(LPI_ERR_ARG, "gemm: dgelu epilogue needs the saved pre-activation");
+    if ((epi == EPI_DGELU_BF16 || epi == EPI_DGELU_F32) && !aux)
+        return set_error(LPI_ERR_ARG, "gemm: dgelu epilogue needs the saved pre-activation");
     if (!out) return set_error(LPI_ERR_ARG, "gemm: null output");
     int bn = tile_n;
     const int sms = num_sms();
@@ -473,15 +513,20 @@ extern "C" int lpi_gemm_bf16(const void* A, const void* B, int M, int N, int K, 
     if (bn != 128 && bn != 256) return set_error(LPI_ERR_ARG, "gemm: tile_n must be 0, 128 or 256");
     if (N % bn) return set_error(LPI_ERR_ARG, "gemm: N=%d not a multiple of tile_n=%d", N, bn);
     CUtensorMap tmA, tmB;
-    if (int rc = make_tmap_2d(&tmA, A, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, M, K, K, BM, BK)) return rc;
-    if (int rc = make_tmap_2d(&tmB, B, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, N, K, K, bn, BK)) return rc;
+    const CUtensorMapDataType dt = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    const int eb = tf32 ? 4 : 2;
+    if (int rc = make_tmap_2d(&tmA, A, dt, eb, M, K, K, BM, bke)) return rc;
+    if (int rc = make_tmap_2d(&tmB, B, dt, eb, N, K, K, bn, bke)) return rc;
     GemmArgs a{};
     a.M = M; a.N = N; a.K = K; a.epi = epi; a.ldo = ldo;
     a.bias = static_cast<const float*>(bias);
     a.resid = static_cast<const float*>(resid);
-    a.aux_bf16 = static_cast<const __nv_bfloat16*>(aux);
-    a.out2_bf16 = static_cast<__nv_bfloat16*>(out2);
-    if (epi == EPI_BIAS_RESID_F32 || epi == EPI_F32 || epi == EPI_ACC_F32 || epi == EPI_BIAS_F32) {
+    if (epi == EPI_DGELU_F32) a.aux_f32 = static_cast<const float*>(aux);
+    else a.aux_bf16 = static_cast<const __nv_bfloat16*>(aux);
+    if (epi == EPI_BIAS_GELU_F32) a.out2_f32 = static_cast<float*>(out2);
+    else a.out2_bf16 = static_cast<__nv_bfloat16*>(out2);
+    if (epi == EPI_BIAS_RESID_F32 || epi == EPI_F32 || epi == EPI_ACC_F32 || epi == EPI_BIAS_F32 || epi == EPI_BIAS_GELU_F32 ||
+        epi == EPI_DGELU_F32) {
         a.out_f32 = static_cast<float*>(out);
         a.out_bf16 = (epi == EPI_BIAS_RESID_F32 || epi == EPI_ACC_F32) ? static_cast<__nv_bfloat16*>(out2) : nullptr;
         a.out2_bf16 = nullptr;
@@ -491,7 +536,20 @@ extern "C" int lpi_gemm_bf16(const void* A, const void* B, int M, int N, int K, 
     const long tiles = long((M + BM - 1) / BM) * (N / bn);
     const int grid = int(tiles < sms ? tiles : sms);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (tf32) return bn == 256 ? launch_epi_tf32<256>(tmA, tmB, a, grid, st) : launch_epi_tf32<128>(tmA, tmB, a, grid, st);
     return bn == 256 ? launch_epi<256>(tmA, tmB, a, grid, st) : launch_epi<128>(tmA, tmB, a, grid, st);
+}
+
+extern "C" int lpi_gemm_bf16(const void* A, const void* B, int M, int N, int K, int epi, const void* bias, const void* resid, void* out,
+                             void* out2, const void* aux, int ldo, int tile_n, void* stream) {
+    if (epi == EPI_BIAS_GELU_F32 || epi == EPI_DGELU_F32)
+        return set_error(LPI_ERR_ARG, "gemm_bf16: epilogue %d is only available for TF32 operands", epi);
+    return gemm_entry(false, A, B, M, N, K, epi, bias, resid, out, out2, aux, ldo, tile_n, stream);
+}
+
+extern "C" int lpi_gemm_tf32(const void* A, const void* B, int M, int N, int K, int epi, const void* bias, const void* resid, void* out,
+                             void* out2, const void* aux, int ldo, int tile_n, void* stream) {
+    return gemm_entry(true, A, B, M, N, K, epi, bias, resid, out, out2, aux, ldo, tile_n, stream);
 }
 
 extern "C" int lpi_sim_topk_chunks(int n_queries, int n_gallery, int* n_chunks_out) {

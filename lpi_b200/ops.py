@@ -10,7 +10,8 @@ import torch
 from . import _lib
 from ._lib import call, ptr, stream_ptr
 
-EPI_BIAS_BF16, EPI_BIAS_GELU_BF16, EPI_BIAS_RESID_F32, EPI_F32, EPI_ACC_F32, EPI_DGELU_BF16, EPI_BF16, EPI_BIAS_F32 = range(8)
+(EPI_BIAS_BF16, EPI_BIAS_GELU_BF16, EPI_BIAS_RESID_F32, EPI_F32, EPI_ACC_F32, EPI_DGELU_BF16, EPI_BF16, EPI_BIAS_F32,
+ EPI_BIAS_GELU_F32, EPI_DGELU_F32) = range(10)
 
 KERNEL_LAUNCHES = 0          # count of lpi kernels launched (bench.py reports it as gpu_launches)
 
@@ -52,6 +53,26 @@ def gemm(a: torch.Tensor, w: torch.Tensor, epi: int, bias: Optional[torch.Tensor
             _chk(t, torch.bfloat16, n)
     call("gemm_bf16", ptr(a), ptr(w), M, N, K, epi, ptr(bias), ptr(resid), ptr(out), ptr(out2), ptr(aux),
          out.stride(0), tile_n, stream_ptr())
+    _count()
+    return out
+
+
+def gemm_tf32(a: torch.Tensor, w: torch.Tensor, epi: int, bias: Optional[torch.Tensor] = None, resid: Optional[torch.Tensor] = None,
+              out: Optional[torch.Tensor] = None, out2: Optional[torch.Tensor] = None, aux: Optional[torch.Tensor] = None,
+              tile_n: int = 0) -> torch.Tensor:
+    """out[M,N] = epilogue(a[M,K] @ w[N,K]^T) with fp32 operands on the TF32 tensor-core path (text tower)."""
+    _lib.require_device()
+    _chk(a, torch.float32, "a")
+    _chk(w, torch.float32, "w")
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K
+    bf16_out = epi in (EPI_BIAS_BF16, EPI_BF16)
+    if out is None:
+        out = torch.empty(M, N, device=a.device, dtype=torch.bfloat16 if bf16_out else torch.float32)
+    _chk(out, torch.bfloat16 if bf16_out else torch.float32, "out")
+    call("gemm_tf32", ptr(a), ptr(w), M, N, K, epi, ptr(bias), ptr(resid), ptr(out), ptr(out2), ptr(aux), out.stride(0), tile_n,
+         stream_ptr())
     _count()
     return out
 
@@ -155,26 +176,28 @@ def l2_normalize(x: torch.Tensor, want_norm: bool = False):
 
 
 # ------------------------------------------------------------------------------------------ attention
-def attn_fwd(qkv: torch.Tensor, B: int, L: int, H: int, causal: bool, want_lse: bool = True):
-    """qkv [B*L, 3*H*64] bf16 -> (out [B*L, H*64] bf16, lse2 [B*H*L] fp32 or None)."""
+def attn_fwd(qkv: torch.Tensor, B: int, L: int, H: int, causal: bool, want_lse: bool = True, want_f32: bool = False):
+    """qkv [B*L, 3*H*64] bf16 -> (out [B*L, H*64] bf16, lse2 [B*H*L] fp32 or None[, out_f32])."""
     _lib.require_device()
     _chk(qkv, torch.bfloat16, "qkv")
     assert qkv.shape == (B * L, 3 * H * 64)
     out = torch.empty(B * L, H * 64, device=qkv.device, dtype=torch.bfloat16)
     lse = torch.empty(B * H * L, device=qkv.device, dtype=torch.float32) if want_lse else None
-    call("attn_fwd", ptr(qkv), ptr(out), ptr(lse), B, L, H, int(causal), stream_ptr())
+    of = torch.empty(B * L, H * 64, device=qkv.device, dtype=torch.float32) if want_f32 else None
+    call("attn_fwd", ptr(qkv), ptr(out), ptr(of), ptr(lse), B, L, H, int(causal), stream_ptr())
     _count()
-    return out, lse
+    return (out, lse, of) if want_f32 else (out, lse)
 
 
-def attn_bwd(qkv, out, d_out, lse, B: int, L: int, H: int, causal: bool, dqkv: Optional[torch.Tensor] = None):
+def attn_bwd(qkv, out, d_out, lse, B: int, L: int, H: int, causal: bool, dqkv: Optional[torch.Tensor] = None, f32: bool = False):
     for t, n in ((qkv, "qkv"), (out, "out"), (d_out, "d_out")):
         _chk(t, torch.bfloat16, n)
     _chk(lse, torch.float32, "lse")
     if dqkv is None:
-        dqkv = torch.empty_like(qkv)
+        dqkv = torch.empty_like(qkv, dtype=torch.float32 if f32 else torch.bfloat16)
     delta = torch.empty(B * H * L, device=qkv.device, dtype=torch.float32)
-    call("attn_bwd", ptr(qkv), ptr(out), ptr(d_out), ptr(lse), ptr(delta), ptr(dqkv), B, L, H, int(causal), stream_ptr())
+    call("attn_bwd", ptr(qkv), ptr(out), ptr(d_out), ptr(lse), ptr(delta), None if f32 else ptr(dqkv), ptr(dqkv) if f32 else None, B, L, H,
+         int(causal), stream_ptr())
     _count(3)
     return dqkv
 

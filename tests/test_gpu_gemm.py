@@ -70,3 +70,28 @@ def test_gemm_rejects_bad_shapes():
     w = torch.zeros(128, 60, device="cuda", dtype=torch.bfloat16)
     with pytest.raises(LpiError):
         ops.gemm(a, w, ops.EPI_F32)
+
+
+@pytest.mark.parametrize("M,N,K", [(77 * 3, 512, 512), (4928, 1536, 512), (1000, 512, 2048), (5, 128, 32)])
+def test_gemm_tf32(M, N, K):
+    """fp32 operands on the TF32 path: error bound = 2^-11 operand rounding (vs 2^-8 for bf16)."""
+    g = torch.Generator().manual_seed(K)
+    a = torch.randn(M, K, generator=g).cuda()
+    w = (torch.randn(N, K, generator=g) * K ** -0.5).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    resid = torch.randn(M, N, generator=g).cuda()
+    ref = a.double() @ w.double().t()
+    out = ops.gemm_tf32(a, w, ops.EPI_F32)
+    tol = 2 ** -9 * float(ref.abs().max())          # two operands rounded to 11 bits each
+    assert (out.double() - ref).abs().max() < tol
+    out = ops.gemm_tf32(a, w, ops.EPI_BIAS_RESID_F32, bias=bias, resid=resid)
+    assert (out.double() - (ref + bias + resid)).abs().max() < tol
+    z = torch.empty(M, N, device="cuda")
+    out = ops.gemm_tf32(a, w, ops.EPI_BIAS_GELU_F32, bias=bias, out2=z)
+    pre = ref + bias
+    assert (z.double() - pre).abs().max() < tol and (out.double() - pre * torch.sigmoid(1.702 * pre)).abs().max() < 2 * tol
+    out = ops.gemm_tf32(a, w, ops.EPI_DGELU_F32, aux=z)
+    s = torch.sigmoid(1.702 * z.double())
+    assert (out.double() - ref * (s * (1 + 1.702 * z.double() * (1 - s)))).abs().max() < 2 * tol
+    outb = ops.gemm_tf32(a, w, ops.EPI_BIAS_BF16, bias=bias)
+    assert outb.dtype == torch.bfloat16 and (outb.double() - pre).abs().max() < 2 ** -8 * float(pre.abs().max())

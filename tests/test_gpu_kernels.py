@@ -66,7 +66,11 @@ def test_attention_fwd_bwd(B, L, H, causal):
     assert (lse.view(B, H, L) - want_lse).abs().max() < 1e-3
     d_out = torch.randn(B * L, D, generator=g).cuda().bfloat16()
     ref.backward(d_out.float())
+    out2, _, of = ops.attn_fwd(qkv, B, L, H, causal, want_f32=True)         # fp32 hand-over for TF32 consumers
+    assert torch.equal(out2, out) and (of - ref).abs().max() < 0.02 * ref.abs().max() and torch.equal(of.bfloat16(), out)
+    dq32 = ops.attn_bwd(qkv, out, d_out, lse, B, L, H, causal, f32=True)
     dqkv = ops.attn_bwd(qkv, out, d_out, lse, B, L, H, causal)
+    assert dq32.dtype == torch.float32 and torch.equal(dq32.bfloat16(), dqkv)
     assert _rel(dqkv.float(), qr.grad) < 2e-2                          # bf16 P / dS / outputs vs fp32 autograd
     for part in range(3):
         sl = slice(part * D, (part + 1) * D)
