@@ -244,17 +244,17 @@ __global__ void inject_prompt_rows_kernel(float* __restrict__ x, const float* __
 
 // ------------------------------------------------------------------------------------------------ encoder heads
 // feat[b] = normalize( LN(x[row_idx[b]]) @ proj ),  proj [D, E] row-major (model.py:254-257, prompt_learner.py:57-61, slinet.py:122,133)
-// One block (256 threads) per HB samples so the projection matrix is read once per HB rows.
+// grid = (ceil(B/HB), E/128): a block normalises HB rows into smem (cheap, recomputed per column slice) and produces a
+// 128-wide slice of the projection for them; the L2 normalisation over E follows in head_norm_kernel.
 constexpr int HB = 4;
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 head_fwd_kernel(const float* __restrict__ x, const int* __restrict__ row_idx, const float* __restrict__ gamma, const float* __restrict__ beta,
-                const float* __restrict__ proj, float* __restrict__ z_out, float* __restrict__ feat_out, int B, int D, int E, float eps) {
-    extern __shared__ float sm[];                    // y[HB][D] | red[HB][8]
+                const float* __restrict__ proj, float* __restrict__ z_out, int B, int D, int E, float eps) {
+    extern __shared__ float sm[];                    // y[HB][D]
     float* y = sm;
-    float* red = sm + HB * D;
     const int b0 = blockIdx.x * HB;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (warp < HB && b0 + warp < B) {                // one warp normalises one row
+    if (b0 + warp < B) {                             // 4 warps: one row each
         const float* xr = x + long(row_idx[b0 + warp]) * D;
         float s = 0.f;
         for (int c = lane; c < D; c += 32) s += xr[c];
@@ -263,41 +263,34 @@ head_fwd_kernel(const float* __restrict__ x, const int* __restrict__ row_idx, co
         for (int c = lane; c < D; c += 32) { const float d = xr[c] - mean; q += d * d; }
         const float rstd = rsqrtf(warp_sum(q) / D + eps);
         for (int c = lane; c < D; c += 32) y[warp * D + c] = (xr[c] - mean) * rstd * gamma[c] + beta[c];
-    } else if (warp < HB) {
+    } else {
         for (int c = lane; c < D; c += 32) y[warp * D + c] = 0.f;
     }
     __syncthreads();
-    float ss[HB];
+    const int e = blockIdx.y * 128 + threadIdx.x;
+    if (e >= E) return;
+    float acc[HB];
 #pragma unroll
-    for (int h = 0; h < HB; ++h) ss[h] = 0.f;
-    for (int e = threadIdx.x; e < E; e += 256) {
-        float acc[HB];
+    for (int h = 0; h < HB; ++h) acc[h] = 0.f;
+#pragma unroll 8
+    for (int k = 0; k < D; ++k) {
+        const float w = proj[long(k) * E + e];
 #pragma unroll
-        for (int h = 0; h < HB; ++h) acc[h] = 0.f;
-        for (int k = 0; k < D; ++k) {
-            const float w = proj[long(k) * E + e];
-#pragma unroll
-            for (int h = 0; h < HB; ++h) acc[h] = fmaf(y[h * D + k], w, acc[h]);
-        }
-#pragma unroll
-        for (int h = 0; h < HB; ++h) {
-            if (b0 + h < B) z_out[long(b0 + h) * E + e] = acc[h];
-            ss[h] += acc[h] * acc[h];
-        }
+        for (int h = 0; h < HB; ++h) acc[h] = fmaf(y[h * D + k], w, acc[h]);
     }
 #pragma unroll
-    for (int h = 0; h < HB; ++h) {
-        const float v = warp_sum(ss[h]);
-        if (lane == 0) red[h * 8 + warp] = v;
-    }
-    __syncthreads();
-    for (int h = 0; h < HB; ++h) {
-        if (b0 + h >= B) break;
-        float tot = 0.f;
-        for (int w = 0; w < 8; ++w) tot += red[h * 8 + w];
-        const float inv = 1.f / sqrtf(tot);
-        for (int e = threadIdx.x; e < E; e += 256) feat_out[long(b0 + h) * E + e] = z_out[long(b0 + h) * E + e] * inv;
-    }
+    for (int h = 0; h < HB; ++h)
+        if (b0 + h < B) z_out[long(b0 + h) * E + e] = acc[h];
+}
+
+// feat[b] = z[b] / ||z[b]||   (one warp per sample)
+__global__ void head_norm_kernel(const float* __restrict__ z, float* __restrict__ feat, int B, int E) {
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (b >= B) return;
+    float ss = 0.f;
+    for (int e = lane; e < E; e += 32) { const float v = z[long(b) * E + e]; ss += v * v; }
+    const float inv = 1.f / sqrtf(warp_sum(ss));
+    for (int e = lane; e < E; e += 32) feat[long(b) * E + e] = z[long(b) * E + e] * inv;
 }
 
 // Backward of the head for one sample per block: (dfeat -> dz via the L2-norm backward) + dz_direct -> dy = dz @ proj^T
@@ -485,9 +478,10 @@ extern "C" int lpi_inject_prompt_rows(float* x, const float* prompt, const int* 
 extern "C" int lpi_head_fwd(const float* x, const int* row_idx, const float* ln_gamma, const float* ln_beta, const float* proj, float* z_out,
                             float* feat_out, int B, int D, int E, float eps, void* stream) {
     if (B <= 0) return LPI_OK;
-    const int smem = (HB * D + HB * 8) * sizeof(float);
-    head_fwd_kernel<<<(B + HB - 1) / HB, 256, smem, static_cast<cudaStream_t>(stream)>>>(x, row_idx, ln_gamma, ln_beta, proj, z_out, feat_out,
-                                                                                        B, D, E, eps);
+    const int smem = HB * D * sizeof(float);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    head_fwd_kernel<<<dim3((B + HB - 1) / HB, (E + 127) / 128), 128, smem, st>>>(x, row_idx, ln_gamma, ln_beta, proj, z_out, B, D, E, eps);
+    head_norm_kernel<<<(B * 32 + 255) / 256, 256, 0, st>>>(z_out, feat_out, B, E);
     return check_launch("head_fwd");
 }
 

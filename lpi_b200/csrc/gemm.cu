@@ -58,7 +58,8 @@ struct Cfg {
     static constexpr int TMEM_COLS = 2 * BN;
     static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
     static constexpr int LIST_OFF = BAR_OFF + 256;
-    static constexpr int SMEM_BYTES = LIST_OFF + BM * TOPK_MAX * 8 + 1024;   // +1024 alignment slack
+    static constexpr int EPI_STAGE_BYTES = 4 * 32 * 32 * 4;                  // MODE_GEMM: per-warp transpose tiles (reuse the list region)
+    static constexpr int SMEM_BYTES = LIST_OFF + (BM * TOPK_MAX * 8 > EPI_STAGE_BYTES ? BM * TOPK_MAX * 8 : EPI_STAGE_BYTES) + 1024;   // +1024 alignment slack
 };
 
 // The sequence of (m0, n0) tiles a CTA walks is a pure function of blockIdx, so each warp role
@@ -127,94 +128,88 @@ __device__ __forceinline__ float quick_gelu_grad(float z) {
     return s * (1.0f + 1.702f * z * (1.0f - s));
 }
 
-// 32 accumulator columns of one output row -> global memory, with the fused epilogue op.
+// Fused epilogue of one 32-row x 32-column accumulator block owned by one warp.
+// tcgen05.ld hands every thread one ROW (32 consecutive columns); writing that straight to global memory makes each warp
+// store instruction touch 32 different rows in 16-byte pieces (and the residual / pre-activation reads likewise): 32 LSU
+// wavefronts per instruction, which ran the GELU / dGELU / residual epilogues 3-4x slower than the MMA main loop.
+// So the block is transposed through a per-warp 4 KB smem tile (128-byte rows, 16-byte chunks XOR-swizzled by row & 7 so
+// both directions are bank-conflict free) using 16-byte accesses only, and all global traffic is issued with 8 lanes
+// covering one row: every instruction moves 4 rows x 128 B (fp32) or 4 x 64 B (bf16) in full sectors.
+__device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+
 template <int EPI>
-__device__ __forceinline__ void epilogue_chunk(const GemmArgs& p, const uint32_t (&r)[32], int row, int col0) {
-    float v[32];
+__device__ __forceinline__ void epilogue_block(const GemmArgs& p, const float4* __restrict__ st, int row0, int col0, int lane) {
+    constexpr bool kBias = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_F32 ||
+                            EPI == EPI_BIAS_GELU_F32);
+    constexpr bool kF32Out = (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_F32 || EPI == EPI_ACC_F32 || EPI == EPI_BIAS_F32 ||
+                              EPI == EPI_BIAS_GELU_F32 || EPI == EPI_DGELU_F32);
+    const int rows = min(32, p.M - row0);                      // warp-uniform
+    if (rows <= 0) return;
+    const int rsub = lane >> 3, c = lane & 7;                  // this lane: rows rsub, rsub+4, ..., columns 4c .. 4c+3
+    const int col = col0 + c * 4;
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (kBias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+    float4 v[8];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-    if (EPI != EPI_F32 && EPI != EPI_ACC_F32 && EPI != EPI_DGELU_BF16 && EPI != EPI_BF16 && EPI != EPI_DGELU_F32) {
-        const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            float4 b = __ldg(b4 + j);
-            v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-        }
+    for (int i = 0; i < 8; ++i) {
+        const int r = i * 4 + rsub;
+        v[i] = f4_add(st[r * 8 + (c ^ (r & 7))], b4);
     }
-    if (row >= p.M) return;
-    const size_t off = size_t(row) * p.ldo + col0;
-    if (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_ACC_F32) {
-        const float4* s4 = reinterpret_cast<const float4*>((EPI == EPI_ACC_F32 ? p.out_f32 : p.resid) + off);
-        float4* d4 = reinterpret_cast<float4*>(p.out_f32 + off);
+    const size_t base = size_t(row0 + rsub) * p.ldo + col;     // + i*4 rows
+    if (kF32Out) {
+        if (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_ACC_F32 || EPI == EPI_DGELU_F32) {
+            const float* src = (EPI == EPI_BIAS_RESID_F32) ? p.resid : (EPI == EPI_ACC_F32 ? p.out_f32 : p.aux_f32);
+            float4 e[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            float4 s = s4[j];
-            v[4 * j] += s.x; v[4 * j + 1] += s.y; v[4 * j + 2] += s.z; v[4 * j + 3] += s.w;
-            d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        }
-        if (p.out_bf16) {   // optional bf16 shadow of the fp32 stream (A operand of the next dgrad GEMM)
-            uint4* o4 = reinterpret_cast<uint4*>(p.out_bf16 + off);
+            for (int i = 0; i < 8; ++i)
+                e[i] = (i * 4 + rsub < rows) ? *reinterpret_cast<const float4*>(src + base + size_t(i * 4) * p.ldo) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-                o4[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                                   pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
-        }
-        return;
-    }
-    if (EPI == EPI_BIAS_GELU_F32) {       // fp32 activations for a TF32 consumer; fp32 pre-activation kept for the backward
-        if (p.out2_f32) {
-            float4* z4 = reinterpret_cast<float4*>(p.out2_f32 + off);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) z4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = quick_gelu(v[j]);
-    }
-    if (EPI == EPI_DGELU_F32) {
-        const float4* z4 = reinterpret_cast<const float4*>(p.aux_f32 + off);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float4 z = z4[j];
-            v[4 * j] *= quick_gelu_grad(z.x); v[4 * j + 1] *= quick_gelu_grad(z.y);
-            v[4 * j + 2] *= quick_gelu_grad(z.z); v[4 * j + 3] *= quick_gelu_grad(z.w);
-        }
-    }
-    if (EPI == EPI_F32 || EPI == EPI_BIAS_F32 || EPI == EPI_BIAS_GELU_F32 || EPI == EPI_DGELU_F32) {
-        float4* d4 = reinterpret_cast<float4*>(p.out_f32 + off);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) d4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        return;
-    }
-    if (EPI == EPI_BIAS_GELU_BF16) {
-        if (p.out2_bf16) {   // keep the pre-activation for the backward pass
-            uint4* z4 = reinterpret_cast<uint4*>(p.out2_bf16 + off);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                z4[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                                   pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = quick_gelu(v[j]);
-    }
-    if (EPI == EPI_DGELU_BF16) {
-        const uint4* z4 = reinterpret_cast<const uint4*>(p.aux_bf16 + off);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            uint4 z = z4[j];
-            const __nv_bfloat162* zz = reinterpret_cast<const __nv_bfloat162*>(&z);
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-                float2 f = __bfloat1622float2(zz[t]);
-                v[8 * j + 2 * t] *= quick_gelu_grad(f.x);
-                v[8 * j + 2 * t + 1] *= quick_gelu_grad(f.y);
+            for (int i = 0; i < 8; ++i) {
+                if (EPI == EPI_DGELU_F32) {
+                    v[i].x *= quick_gelu_grad(e[i].x); v[i].y *= quick_gelu_grad(e[i].y);
+                    v[i].z *= quick_gelu_grad(e[i].z); v[i].w *= quick_gelu_grad(e[i].w);
+                } else {
+                    v[i] = f4_add(v[i], e[i]);
+                }
             }
         }
-    }
-    uint4* o4 = reinterpret_cast<uint4*>(p.out_bf16 + off);
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-        o4[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                           pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
+        for (int i = 0; i < 8; ++i) {
+            if (i * 4 + rsub >= rows) continue;
+            const size_t off = base + size_t(i * 4) * p.ldo;
+            if (EPI == EPI_BIAS_GELU_F32) {
+                if (p.out2_f32) *reinterpret_cast<float4*>(p.out2_f32 + off) = v[i];
+                v[i] = make_float4(quick_gelu(v[i].x), quick_gelu(v[i].y), quick_gelu(v[i].z), quick_gelu(v[i].w));
+            }
+            *reinterpret_cast<float4*>(p.out_f32 + off) = v[i];
+            if ((EPI == EPI_BIAS_RESID_F32 || EPI == EPI_ACC_F32) && p.out_bf16)
+                *reinterpret_cast<uint2*>(p.out_bf16 + off) = make_uint2(pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));
+        }
+    } else {
+        if (EPI == EPI_DGELU_BF16) {
+            uint2 e[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                e[i] = (i * 4 + rsub < rows) ? *reinterpret_cast<const uint2*>(p.aux_bf16 + base + size_t(i * 4) * p.ldo) : make_uint2(0u, 0u);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float2 z0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&e[i].x));
+                const float2 z1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&e[i].y));
+                v[i].x *= quick_gelu_grad(z0.x); v[i].y *= quick_gelu_grad(z0.y);
+                v[i].z *= quick_gelu_grad(z1.x); v[i].w *= quick_gelu_grad(z1.y);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (i * 4 + rsub >= rows) continue;
+            const size_t off = base + size_t(i * 4) * p.ldo;
+            if (EPI == EPI_BIAS_GELU_BF16) {
+                if (p.out2_bf16) *reinterpret_cast<uint2*>(p.out2_bf16 + off) = make_uint2(pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));
+                v[i] = make_float4(quick_gelu(v[i].x), quick_gelu(v[i].y), quick_gelu(v[i].z), quick_gelu(v[i].w));
+            }
+            *reinterpret_cast<uint2*>(p.out_bf16 + off) = make_uint2(pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));
+        }
+    }
 }
 
 // TF32 = true: fp32 operands in memory (32 elements = 128 B per swizzle row), tcgen05.mma kind::tf32 (K = 8 per instruction)
@@ -337,7 +332,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 LPI_TMEM_LD_X32(taddr, r);
                 tmem_ld_wait();
                 if (MODE == MODE_GEMM) {
-                    epilogue_chunk<EPI>(p, r, row, n0 + c * 32);
+                    float4* stg = reinterpret_cast<float4*>(smem_gen + C::LIST_OFF) + (warp - 2) * 32 * 8;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)          // own row, 16-byte chunk j -> swizzled slot
+                        stg[lane * 8 + (j ^ (lane & 7))] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                                       __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+                    __syncwarp();
+                    epilogue_block<EPI>(p, stg, m0 + quad * 32, n0 + c * 32, lane);
+                    __syncwarp();
                 } else {
                     const int col0 = n0 + c * 32;
                     if (col0 + 32 > p.N) {            // ragged gallery tail: rows past N were zero-filled by TMA
