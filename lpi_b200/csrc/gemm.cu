@@ -17,6 +17,7 @@
 //                   of its query row ordered by (score desc, gallery index asc).
 #include "ptx.cuh"
 #include "lpi_internal.h"
+#include <stdlib.h>
 
 namespace lpi {
 
@@ -122,9 +123,22 @@ struct TileWalk {
     }
 };
 
-__device__ __forceinline__ float quick_gelu(float z) { return z / (1.0f + __expf(-1.702f * z)); }
+// QuickGELU z * sigmoid(1.702 z) (model.py:163-165) and its derivative.  The plain `/` compiles to the IEEE division
+// sequence (FCHK + a slow-path CALL per element), which made the GELU epilogues 4x slower than the MMA loop, so:
+//   bf16 outputs : sigmoid(x) = 0.5 tanh.approx(0.5 x) + 0.5 -- ONE MUFU op per element, |error| <= 2^-11 (output rounding is 2^-9)
+//   fp32 outputs : 1 / (1 + exp(-x)) with ex2.approx + rcp.approx (2 MUFU ops, ~2 ulp)
+template <bool PRECISE>
+__device__ __forceinline__ float sigmoid_fast(float x) {
+    if (PRECISE) return __fdividef(1.0f, 1.0f + __expf(-x));
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
+    return fmaf(0.5f, t, 0.5f);
+}
+template <bool PRECISE = false>
+__device__ __forceinline__ float quick_gelu(float z) { return z * sigmoid_fast<PRECISE>(1.702f * z); }
+template <bool PRECISE = false>
 __device__ __forceinline__ float quick_gelu_grad(float z) {
-    float s = 1.0f / (1.0f + __expf(-1.702f * z));
+    const float s = sigmoid_fast<PRECISE>(1.702f * z);
     return s * (1.0f + 1.702f * z * (1.0f - s));
 }
 
@@ -166,8 +180,8 @@ __device__ __forceinline__ void epilogue_block(const GemmArgs& p, const float4* 
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 if (EPI == EPI_DGELU_F32) {
-                    v[i].x *= quick_gelu_grad(e[i].x); v[i].y *= quick_gelu_grad(e[i].y);
-                    v[i].z *= quick_gelu_grad(e[i].z); v[i].w *= quick_gelu_grad(e[i].w);
+                    v[i].x *= quick_gelu_grad<true>(e[i].x); v[i].y *= quick_gelu_grad<true>(e[i].y);
+                    v[i].z *= quick_gelu_grad<true>(e[i].z); v[i].w *= quick_gelu_grad<true>(e[i].w);
                 } else {
                     v[i] = f4_add(v[i], e[i]);
                 }
@@ -179,7 +193,7 @@ __device__ __forceinline__ void epilogue_block(const GemmArgs& p, const float4* 
             const size_t off = base + size_t(i * 4) * p.ldo;
             if (EPI == EPI_BIAS_GELU_F32) {
                 if (p.out2_f32) *reinterpret_cast<float4*>(p.out2_f32 + off) = v[i];
-                v[i] = make_float4(quick_gelu(v[i].x), quick_gelu(v[i].y), quick_gelu(v[i].z), quick_gelu(v[i].w));
+                v[i] = make_float4(quick_gelu<true>(v[i].x), quick_gelu<true>(v[i].y), quick_gelu<true>(v[i].z), quick_gelu<true>(v[i].w));
             }
             *reinterpret_cast<float4*>(p.out_f32 + off) = v[i];
             if ((EPI == EPI_BIAS_RESID_F32 || EPI == EPI_ACC_F32) && p.out_bf16)
@@ -397,6 +411,262 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
+// ================================================================================================================
+// CTA-pair variant (cta_group::2): two CTAs on the two SMs of a TPC execute ONE tcgen05.mma with M = 256, N = 256.
+// Each CTA holds its own 128 rows of A and HALF of the B tile (128 of the 256 N rows), so per CTA the L2 -> smem traffic of
+// a 128 x 256 x K output block drops from (128 + 256) K to (128 + 128) K elements -- the 1-CTA kernel is bound by that
+// traffic (profiles/r1_scorer_v1_ncu.md: ~9 TB/s of TMA at 729 TFLOP/s).  In MODE_TOPK the query tile additionally stays
+// RESIDENT in shared memory for the whole gallery chunk (128 KB for d = 512), leaving only the half gallery tile to stream:
+// 128 KB per 33.5 MFLOP per CTA = 262 FLOP/B.
+//
+// Protocol (CUTLASS-style 2SM pipeline): both CTAs issue their own TMA loads with .cta_group::2 so the bytes complete on
+// the LEADER's (cluster rank 0) full barrier; the leader's single MMA thread issues the MMAs, whose commits are multicast to
+// the empty / accumulator-full barriers of BOTH CTAs; every CTA's epilogue warps drain their own TMEM lanes (their 128 rows)
+// and release the accumulator on the leader's barrier (remote arrive for the peer).
+// ================================================================================================================
+template <int MODE>
+struct PairCfg {
+    static constexpr int BN = 256;
+    static constexpr int A_BYTES = BM * 128;                 // one k-block of A: 128 rows x 128 B
+    static constexpr int BH_BYTES = 128 * 128;               // half B tile: 128 rows x 128 B
+    static constexpr int A_RESIDENT_KB = 8;                  // MODE_TOPK: up to 8 k-blocks (dim <= 512) stay resident
+    static constexpr int STAGE_BYTES = (MODE == MODE_GEMM) ? A_BYTES + BH_BYTES : BH_BYTES;
+    static constexpr int STAGES = (MODE == MODE_GEMM) ? 6 : 5;
+    static constexpr int RING_OFF = (MODE == MODE_GEMM) ? 0 : A_RESIDENT_KB * A_BYTES;
+    static constexpr int BAR_OFF = RING_OFF + STAGES * STAGE_BYTES;
+    static constexpr int LIST_OFF = BAR_OFF + 256;
+    static constexpr int TAIL = (BM * TOPK_MAX * 8 > 4 * 32 * 32 * 4) ? BM * TOPK_MAX * 8 : 4 * 32 * 32 * 4;
+    static constexpr int SMEM_BYTES = LIST_OFF + TAIL + 1024;
+    static constexpr int TMEM_COLS = 512;
+};
+
+template <int MODE, int EPI, bool TF32>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs p) {
+    using C = PairCfg<MODE>;
+    constexpr int BN = C::BN;
+    constexpr int BKE = TF32 ? 32 : BK;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;      // identical in both CTAs
+    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t bar_base = smem_base + C::BAR_OFF;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (C::STAGES + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * C::STAGES + 2 + a); };
+    const uint32_t afull_bar = bar_base + 8u * (2 * C::STAGES + 4);       // MODE_TOPK: resident query tile landed / may be overwritten
+    const uint32_t aempty_bar = bar_base + 8u * (2 * C::STAGES + 5);
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + C::BAR_OFF + 8 * (2 * C::STAGES + 6));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    const int num_k = p.K / BKE;
+    const int num_m = (p.M + BM - 1) / BM, num_mp = (num_m + 1) / 2, num_n = (p.N + BN - 1) / BN;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+    }
+    if (warp == 1) {
+        if (lane == 0) {
+            for (int s = 0; s < C::STAGES; ++s) {
+                mbar_init(full_bar(s), 1);       // leader's own arrive.expect_tx (bytes of both CTAs)
+                mbar_init(empty_bar(s), 1);      // multicast commit
+            }
+            for (int a = 0; a < 2; ++a) {
+                mbar_init(tfull_bar(a), 1);      // multicast commit
+                mbar_init(tempty_bar(a), 8);     // 4 epilogue warps x 2 CTAs (only the leader's copy is used)
+            }
+            mbar_init(afull_bar, 1);
+            mbar_init(aempty_bar, 1);
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc_pair<C::TMEM_COLS>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                          // peer barriers initialised before any remote arrive / multicast commit
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // ---- work decomposition: a pure function of (cluster_id, rank), re-derived by every role
+    // GEMM : cluster tile t -> (mp = t % num_mp, nt = t / num_mp); this CTA owns rows (2 mp + rank) * 128
+    // TOPK : item i -> (qp = i % num_mp, chunk = i / num_mp); gallery tiles [chunk * tpc, min(num_n, (chunk + 1) * tpc))
+    const int total = (MODE == MODE_GEMM) ? num_mp * num_n : num_mp * p.n_chunks;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer (one thread per CTA)
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0, aphase = 0;
+            for (int t = cluster_id; t < total; t += n_clusters) {
+                const int mp = t % num_mp, second = t / num_mp;
+                const int m0 = (2 * mp + int(rank)) * BM;
+                int n_begin, n_end;
+                if (MODE == MODE_GEMM) { n_begin = second; n_end = second + 1; }
+                else {
+                    n_begin = second * p.tiles_per_chunk;
+                    n_end = min(num_n, n_begin + p.tiles_per_chunk);
+                    // resident query tile: all k-blocks once per item, after the previous item's MMAs retired
+                    mbar_wait(aempty_bar, aphase ^ 1);
+                    if (leader) mbar_arrive_expect_tx(afull_bar, 2u * num_k * C::A_BYTES);
+                    for (int kb = 0; kb < num_k; ++kb) tma_load_2d_pair(smem_base + kb * C::A_BYTES, &tmA, afull_bar, kb * BKE, m0);
+                    aphase ^= 1;
+                }
+                for (int nt = n_begin; nt < n_end; ++nt) {
+                    const int n0 = nt * BN + int(rank) * 128;       // this CTA streams its half of the B tile
+                    for (int kb = 0; kb < num_k; ++kb) {
+                        mbar_wait(empty_bar(stage), phase ^ 1);
+                        if (leader) mbar_arrive_expect_tx(full_bar(stage), 2u * C::STAGE_BYTES);
+                        const uint32_t sa = smem_base + C::RING_OFF + stage * C::STAGE_BYTES;
+                        if (MODE == MODE_GEMM) {
+                            tma_load_2d_pair(sa, &tmA, full_bar(stage), kb * BKE, m0);
+                            tma_load_2d_pair(sa + C::A_BYTES, &tmB, full_bar(stage), kb * BKE, n0);
+                        } else {
+                            tma_load_2d_pair(sa, &tmB, full_bar(stage), kb * BKE, n0);
+                        }
+                        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer (leader CTA, single thread)
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc = make_idesc(TF32 ? kFmtTF32 : kFmtBF16, 2 * BM, BN, 0, 0);
+            int stage = 0, acc = 0;
+            uint32_t phase = 0, acc_phase = 0, aphase = 0;
+            for (int t = cluster_id; t < total; t += n_clusters) {
+                const int second = t / num_mp;
+                int n_begin, n_end;
+                if (MODE == MODE_GEMM) { n_begin = second; n_end = second + 1; }
+                else {
+                    n_begin = second * p.tiles_per_chunk;
+                    n_end = min(num_n, n_begin + p.tiles_per_chunk);
+                    mbar_wait(afull_bar, aphase);
+                    aphase ^= 1;
+                    tc_fence_after();
+                }
+                for (int nt = n_begin; nt < n_end; ++nt) {
+                    mbar_wait(tempty_bar(acc), acc_phase ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + acc * BN;
+                    for (int kb = 0; kb < num_k; ++kb) {
+                        mbar_wait(full_bar(stage), phase);
+                        tc_fence_after();
+                        const uint32_t sa = smem_base + C::RING_OFF + stage * C::STAGE_BYTES;
+                        const uint64_t da = make_desc_kmajor_sw128(MODE == MODE_GEMM ? sa : smem_base + kb * C::A_BYTES);
+                        const uint64_t db = make_desc_kmajor_sw128(MODE == MODE_GEMM ? sa + C::A_BYTES : sa);
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            if (TF32) umma_tf32_ss_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                            else umma_f16_ss_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        }
+                        umma_commit_pair(empty_bar(stage));
+                        if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    umma_commit_pair(tfull_bar(acc));
+                    if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                }
+                if (MODE == MODE_TOPK) umma_commit_pair(aempty_bar);     // every MMA reading the resident tile has retired
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue warps (2..5) of BOTH CTAs: own 128 rows
+        const int quad = warp & 3;
+        const int r_local = quad * 32 + lane;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        float* l_sc = reinterpret_cast<float*>(smem_gen + C::LIST_OFF);
+        int* l_id = reinterpret_cast<int*>(smem_gen + C::LIST_OFF + BM * TOPK_MAX * 4);
+        const uint32_t tempty_leader0 = mapa_u32(tempty_bar(0), 0), tempty_leader1 = mapa_u32(tempty_bar(1), 0);
+        for (int t = cluster_id; t < total; t += n_clusters) {
+            const int mp = t % num_mp, second = t / num_mp;
+            const int m0 = (2 * mp + int(rank)) * BM;
+            const int row = m0 + r_local;
+            int n_begin, n_end;
+            if (MODE == MODE_GEMM) { n_begin = second; n_end = second + 1; }
+            else { n_begin = second * p.tiles_per_chunk; n_end = min(num_n, n_begin + p.tiles_per_chunk); }
+            float thr = -INFINITY;
+            int cnt = 0;
+            for (int nt = n_begin; nt < n_end; ++nt) {
+                const int n0 = nt * BN;
+                mbar_wait(tfull_bar(acc), acc_phase);
+                tc_fence_after();
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t r[32];
+                    const uint32_t taddr = tmem_base + uint32_t(acc * BN + c * 32) + (uint32_t(quad * 32) << 16);
+                    LPI_TMEM_LD_X32(taddr, r);
+                    tmem_ld_wait();
+                    if (MODE == MODE_GEMM) {
+                        float4* stg = reinterpret_cast<float4*>(smem_gen + C::LIST_OFF) + (warp - 2) * 32 * 8;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            stg[lane * 8 + (j ^ (lane & 7))] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                                           __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+                        __syncwarp();
+                        epilogue_block<EPI>(p, stg, m0 + quad * 32, n0 + c * 32, lane);
+                        __syncwarp();
+                    } else {
+                        const int col0 = n0 + c * 32;
+                        if (col0 + 32 > p.N) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (col0 + j >= p.N) r[j] = 0xff800000u;
+                        }
+                        float m = __uint_as_float(r[0]);
+#pragma unroll
+                        for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(r[j]));
+                        if (m > thr) {
+                            const int k = p.k;
+#pragma unroll 1
+                            for (int j = 0; j < 32; ++j) {
+                                const float v = __uint_as_float(r[j]);
+                                if (v > thr) {
+                                    int pos = cnt < k ? cnt : k - 1;
+                                    while (pos > 0 && l_sc[(pos - 1) * BM + r_local] < v) {
+                                        l_sc[pos * BM + r_local] = l_sc[(pos - 1) * BM + r_local];
+                                        l_id[pos * BM + r_local] = l_id[(pos - 1) * BM + r_local];
+                                        --pos;
+                                    }
+                                    l_sc[pos * BM + r_local] = v;
+                                    l_id[pos * BM + r_local] = int(p.gallery_offset) + col0 + j;
+                                    if (cnt < k) ++cnt;
+                                    if (cnt == k) thr = l_sc[(k - 1) * BM + r_local];
+                                }
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(acc == 0 ? tempty_leader0 : tempty_leader1);
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+            if (MODE == MODE_TOPK && row < p.M) {
+                float* os = p.topk_scores + (size_t(second) * p.M + row) * p.k;
+                int* oi = p.topk_idx + (size_t(second) * p.M + row) * p.k;
+                for (int j = 0; j < p.k; ++j) {
+                    os[j] = j < cnt ? l_sc[j * BM + r_local] : -INFINITY;
+                    oi[j] = j < cnt ? l_id[j * BM + r_local] : 0x7fffffff;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                          // nobody frees TMEM / exits while the peer may still touch this CTA
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_pair<C::TMEM_COLS>(tmem_base);
+    }
+}
+
 // ------------------------------------------------------------------------------------ host side
 static PFN_encodeTiled g_encode = nullptr;
 
@@ -453,6 +723,49 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(LPI_ERR_CUDA, "gemm launch: %s", cudaGetErrorString(e));
     return 0;
+}
+
+template <int MODE, int EPI, bool TF32>
+static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, int n_clusters, cudaStream_t st) {
+    auto kern = gemm_pair_kernel<MODE, EPI, TF32>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<MODE>::SMEM_BYTES);
+        if (e != cudaSuccess) return set_error(LPI_ERR_CUDA, "cudaFuncSetAttribute(pair): %s", cudaGetErrorString(e));
+        configured = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * n_clusters);
+    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.dynamicSmemBytes = PairCfg<MODE>::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, a);
+    if (e != cudaSuccess) return set_error(LPI_ERR_CUDA, "pair gemm launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+template <bool TF32>
+static int launch_pair_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, int n_clusters, cudaStream_t st) {
+    switch (a.epi) {
+        case EPI_BIAS_BF16: return launch_pair<MODE_GEMM, EPI_BIAS_BF16, TF32>(tmA, tmB, a, n_clusters, st);
+        case EPI_BIAS_RESID_F32: return launch_pair<MODE_GEMM, EPI_BIAS_RESID_F32, TF32>(tmA, tmB, a, n_clusters, st);
+        case EPI_F32: return launch_pair<MODE_GEMM, EPI_F32, TF32>(tmA, tmB, a, n_clusters, st);
+        case EPI_BF16: return launch_pair<MODE_GEMM, EPI_BF16, TF32>(tmA, tmB, a, n_clusters, st);
+        case EPI_BIAS_GELU_BF16: if (!TF32) return launch_pair<MODE_GEMM, EPI_BIAS_GELU_BF16, false>(tmA, tmB, a, n_clusters, st); break;
+        case EPI_DGELU_BF16: if (!TF32) return launch_pair<MODE_GEMM, EPI_DGELU_BF16, false>(tmA, tmB, a, n_clusters, st); break;
+        case EPI_BIAS_F32: if (!TF32) return launch_pair<MODE_GEMM, EPI_BIAS_F32, false>(tmA, tmB, a, n_clusters, st); break;
+        case EPI_ACC_F32: if (!TF32) return launch_pair<MODE_GEMM, EPI_ACC_F32, false>(tmA, tmB, a, n_clusters, st); break;
+        case EPI_BIAS_GELU_F32: if (TF32) return launch_pair<MODE_GEMM, EPI_BIAS_GELU_F32, true>(tmA, tmB, a, n_clusters, st); break;
+        case EPI_DGELU_F32: if (TF32) return launch_pair<MODE_GEMM, EPI_DGELU_F32, true>(tmA, tmB, a, n_clusters, st); break;
+    }
+    return set_error(LPI_ERR_ARG, "epilogue %d is not available for this operand type", a.epi);
 }
 
 template <int BN>
@@ -512,13 +825,14 @@ static int gemm_entry(bool tf32, const void* A, const void* B, int M, int N, int
         };
         bn = (N % 256 == 0 && eff(256) + 0.03 >= eff(128)) ? 256 : 128;   // prefer the wide tile unless quantisation hurts
     }
-    if (bn != 128 && bn != 256) return set_error(LPI_ERR_ARG, "gemm: tile_n must be 0, 128 or 256");
-    if (N % bn) return set_error(LPI_ERR_ARG, "gemm: N=%d not a multiple of tile_n=%d", N, bn);
+    const bool pair = (bn == 512);               // CTA-pair kernel: 256 x 256 tile over two SMs (cta_group::2)
+    if (bn != 128 && bn != 256 && bn != 512) return set_error(LPI_ERR_ARG, "gemm: tile_n must be 0, 128, 256 or 512 (CTA pair)");
+    if (N % (pair ? 256 : bn)) return set_error(LPI_ERR_ARG, "gemm: N=%d not a multiple of the tile width (tile_n=%d)", N, bn);
     CUtensorMap tmA, tmB;
     const CUtensorMapDataType dt = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     const int eb = tf32 ? 4 : 2;
     if (int rc = make_tmap_2d(&tmA, A, dt, eb, M, K, K, BM, bke)) return rc;
-    if (int rc = make_tmap_2d(&tmB, B, dt, eb, N, K, K, bn, bke)) return rc;
+    if (int rc = make_tmap_2d(&tmB, B, dt, eb, N, K, K, pair ? 128 : bn, bke)) return rc;
     GemmArgs a{};
     a.M = M; a.N = N; a.K = K; a.epi = epi; a.ldo = ldo;
     a.bias = static_cast<const float*>(bias);
@@ -535,9 +849,14 @@ static int gemm_entry(bool tf32, const void* A, const void* B, int M, int N, int
     } else {
         a.out_bf16 = static_cast<__nv_bfloat16*>(out);
     }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (pair) {
+        const long ctiles = long(((M + BM - 1) / BM + 1) / 2) * (N / 256);
+        const int n_clusters = int(ctiles < sms / 2 ? ctiles : sms / 2);
+        return tf32 ? launch_pair_epi<true>(tmA, tmB, a, n_clusters, st) : launch_pair_epi<false>(tmA, tmB, a, n_clusters, st);
+    }
     const long tiles = long((M + BM - 1) / BM) * (N / bn);
     const int grid = int(tiles < sms ? tiles : sms);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (tf32) return bn == 256 ? launch_epi_tf32<256>(tmA, tmB, a, grid, st) : launch_epi_tf32<128>(tmA, tmB, a, grid, st);
     return bn == 256 ? launch_epi<256>(tmA, tmB, a, grid, st) : launch_epi<128>(tmA, tmB, a, grid, st);
 }
@@ -554,10 +873,22 @@ extern "C" int lpi_gemm_tf32(const void* A, const void* B, int M, int N, int K, 
     return gemm_entry(true, A, B, M, N, K, epi, bias, resid, out, out2, aux, ldo, tile_n, stream);
 }
 
+static bool scorer_pair_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("LPI_SCORER_PAIR");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
 extern "C" int lpi_sim_topk_chunks(int n_queries, int n_gallery, int* n_chunks_out) {
-    // Work items = query tiles x gallery chunks; pick the chunk count that fills whole waves of SMs.
-    const int sms = num_sms();
-    const int qt = (n_queries + BM - 1) / BM;
+    // Work items = query tiles (tile PAIRS for the CTA-pair kernel) x gallery chunks; pick the chunk count that fills
+    // whole waves of SMs (clusters).
+    const bool pair = scorer_pair_enabled();
+    const int sms = pair ? num_sms() / 2 : num_sms();
+    const int qt1 = (n_queries + BM - 1) / BM;
+    const int qt = pair ? (qt1 + 1) / 2 : qt1;
     const int nt = (n_gallery + 255) / 256;
     int best = 1;
     double best_eff = 0;
@@ -583,9 +914,10 @@ extern "C" int lpi_sim_topk_bf16(const void* Q, const void* G, int n_queries, in
     if (gallery_offset + n_gallery > 0x7fffffffLL) return set_error(LPI_ERR_ARG, "sim_topk: gallery index exceeds int32");
     const int nt = (n_gallery + 255) / 256;
     if (n_chunks > nt) return set_error(LPI_ERR_ARG, "sim_topk: n_chunks=%d > gallery tiles=%d", n_chunks, nt);
+    const bool pair = scorer_pair_enabled() && dim <= PairCfg<MODE_TOPK>::A_RESIDENT_KB * BK;   // query tile must fit resident
     CUtensorMap tmA, tmB;
     if (int rc = make_tmap_2d(&tmA, Q, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, n_queries, dim, dim, BM, BK)) return rc;
-    if (int rc = make_tmap_2d(&tmB, G, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, n_gallery, dim, dim, 256, BK)) return rc;
+    if (int rc = make_tmap_2d(&tmB, G, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, n_gallery, dim, dim, pair ? 128 : 256, BK)) return rc;
     GemmArgs a{};
     a.M = n_queries; a.N = n_gallery; a.K = dim;
     a.k = k; a.n_chunks = n_chunks;
@@ -595,8 +927,13 @@ extern "C" int lpi_sim_topk_bf16(const void* Q, const void* G, int n_queries, in
     a.gallery_offset = gallery_offset;
     a.topk_scores = part_scores;
     a.topk_idx = part_idx;
-    const long items = long((n_queries + BM - 1) / BM) * n_chunks;
     const int sms = num_sms();
+    if (pair) {
+        const long items = long(((n_queries + BM - 1) / BM + 1) / 2) * n_chunks;
+        const int n_clusters = int(items < sms / 2 ? items : sms / 2);
+        return launch_pair<MODE_TOPK, EPI_F32, false>(tmA, tmB, a, n_clusters, static_cast<cudaStream_t>(stream));
+    }
+    const long items = long((n_queries + BM - 1) / BM) * n_chunks;
     const int grid = int(items < sms ? items : sms);
     return launch<MODE_TOPK, 256, EPI_F32>(tmA, tmB, a, grid, static_cast<cudaStream_t>(stream));
 }

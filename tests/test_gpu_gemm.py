@@ -50,9 +50,9 @@ def _case(M, N, K, epi, tile_n, seed=0):
 
 @pytest.mark.parametrize("M,N,K", [(100, 128, 64), (300, 512, 512), (4928, 1536, 512), (13632, 2304, 768),
                                    (13632, 768, 3072), (1, 128, 64)])
-@pytest.mark.parametrize("tile_n", [0, 128, 256])
+@pytest.mark.parametrize("tile_n", [0, 128, 256, 512])
 def test_gemm_shapes(M, N, K, tile_n):
-    if tile_n and N % tile_n:
+    if tile_n and N % min(tile_n, 256):
         pytest.skip("N not a multiple of the tile")
     _case(M, N, K, ops.EPI_F32, tile_n)
 
@@ -61,6 +61,8 @@ def test_gemm_shapes(M, N, K, tile_n):
 def test_gemm_epilogues(epi):
     _case(1000, 768, 768, epi, 0)
     _case(333, 512, 2048, epi, 128, seed=1)
+    _case(1000, 768, 768, epi, 512, seed=2)          # CTA-pair kernel (cta_group::2), odd number of M tiles
+    _case(13632, 768, 3072, epi, 512, seed=3)
 
 
 def test_gemm_rejects_bad_shapes():

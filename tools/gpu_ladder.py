@@ -150,7 +150,7 @@ def rung_bench_gemm():
                       (4928, 512, 2048), (8192, 8192, 8192)]:
         a = torch.randn(M, K, device="cuda").bfloat16()
         w = torch.randn(N, K, device="cuda").bfloat16()
-        for bn in (128, 256):
+        for bn in (128, 256, 512):
             out = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
             for _ in range(3):
                 ops.gemm(a, w, ops.EPI_BF16, out=out, tile_n=bn)
@@ -176,7 +176,7 @@ def rung_bench_gemm():
 def rung_bench_scorer():
     import torch
     from lpi_b200 import ops
-    for (nq, ng) in [(25000, 100000), (25000, 1000000)]:
+    for (nq, ng) in [(25000, 100000), (25000, 1000000), (25000, 5000000)]:
         q = torch.randn(nq, 512, device="cuda").bfloat16()
         g = torch.randn(ng, 512, device="cuda").bfloat16()
         for _ in range(2):
