@@ -329,7 +329,7 @@ def run_b200(args):
                         "ms_per_step": e2e_ms, "steps": e2e_steps},
                 "gpu_launches": launches,
                 "clocks": clocks,
-                "roofline": {"bound": "tensor", "kernel": "gemm_tn_kernel<MODE_TOPK,256>", "achieved": ach, "peak": peaks["tflops"],
+                "roofline": {"bound": "tensor", "kernel": "gemm_pair_kernel<MODE_TOPK> (cta_group::2, resident query tile)", "achieved": ach, "peak": peaks["tflops"],
                              "unit": "TFLOP/s", "frac": ach / peaks["tflops"], "traffic": traffic,
                              "peak_source": peaks["source"] + " (sustained cuBLAS bf16)", "kernel_ms": kern_ms,
                              "flops_per_launch": flops,

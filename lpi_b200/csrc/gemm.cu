@@ -226,6 +226,61 @@ __device__ __forceinline__ void epilogue_block(const GemmArgs& p, const float4* 
     }
 }
 
+// ------------------------------------------------------------------------------------------------ running top-k (MODE_TOPK)
+// One epilogue thread owns one query row; its sorted list (score desc, gallery index asc) lives in shared memory,
+// column-major [j][row].  Insertion is rare after warm-up (~k ln(N/k) per row over the whole gallery) and stays out of line,
+// so the hot path is: 64 accumulator columns -> max tree -> one compare.  The accumulator registers are only ever indexed
+// with compile-time constants (a dynamic r[j] forces the whole array into local memory: 512 B of STL per thread per chunk,
+// which showed up as 60 % L1 throughput in the first capture).
+struct TopkState {
+    float* sc;      // [TOPK_MAX][BM]
+    int* id;
+    int row;        // r_local
+    int k;
+    int cnt;
+    float thr;
+};
+struct TopkCT { int cnt; float thr; };      // returned by value so both stay in registers across the out-of-line call
+
+__device__ __noinline__ TopkCT topk_insert(float* sc, int* id, int row, int k, int cnt, float v, int gidx) {
+    int pos = cnt < k ? cnt : k - 1;
+    while (pos > 0 && sc[(pos - 1) * BM + row] < v) {            // strict: an equal score with a larger index never displaces
+        sc[pos * BM + row] = sc[(pos - 1) * BM + row];
+        id[pos * BM + row] = id[(pos - 1) * BM + row];
+        --pos;
+    }
+    sc[pos * BM + row] = v;
+    id[pos * BM + row] = gidx;
+    if (cnt < k) ++cnt;
+    return {cnt, cnt == k ? sc[(k - 1) * BM + row] : -INFINITY};
+}
+
+template <int NCOL>
+__device__ __forceinline__ void topk_consume(TopkState& st, uint32_t (&r)[NCOL], int col0, int n_valid, int gidx0) {
+    if (col0 + NCOL > n_valid) {                  // ragged gallery tail: rows past N were zero-filled by TMA
+#pragma unroll
+        for (int j = 0; j < NCOL; ++j)
+            if (col0 + j >= n_valid) r[j] = 0xff800000u;   // -inf
+    }
+    float m0 = __uint_as_float(r[0]), m1 = __uint_as_float(r[1]);
+#pragma unroll
+    for (int j = 2; j < NCOL; j += 2) {           // two independent max chains
+        m0 = fmaxf(m0, __uint_as_float(r[j]));
+        m1 = fmaxf(m1, __uint_as_float(r[j + 1]));
+    }
+    if (fmaxf(m0, m1) > st.thr) {
+#pragma unroll
+        for (int j = 0; j < NCOL; ++j) {
+            const float v = __uint_as_float(r[j]);
+            if (v > st.thr) {
+                const TopkCT ct = topk_insert(st.sc, st.id, st.row, st.k, st.cnt, v, gidx0 + col0 + j);
+                st.cnt = ct.cnt;
+                st.thr = ct.thr;
+            }
+        }
+    }
+}
+
 // TF32 = true: fp32 operands in memory (32 elements = 128 B per swizzle row), tcgen05.mma kind::tf32 (K = 8 per instruction)
 template <int MODE, int BN, int EPI, bool TF32 = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
@@ -329,23 +384,20 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint32_t acc_phase = 0;
         int m0, n0;
         bool first, last;
-        // MODE_TOPK running state: sorted list (desc score, asc index) in smem, column-major [j][row]
-        float* l_sc = reinterpret_cast<float*>(smem_gen + C::LIST_OFF);
-        int* l_id = reinterpret_cast<int*>(smem_gen + C::LIST_OFF + BM * TOPK_MAX * 4);
-        float thr = -INFINITY;
-        int cnt = 0;
+        TopkState tk{reinterpret_cast<float*>(smem_gen + C::LIST_OFF), reinterpret_cast<int*>(smem_gen + C::LIST_OFF + BM * TOPK_MAX * 4),
+                     r_local, p.k, 0, -INFINITY};
         while (walk.next(m0, n0, first, last)) {
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
             const int row = m0 + r_local;
-            if (MODE == MODE_TOPK && first) { thr = -INFINITY; cnt = 0; }
+            if (MODE == MODE_TOPK && first) { tk.thr = -INFINITY; tk.cnt = 0; }
+            if (MODE == MODE_GEMM) {
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t r[32];
-                const uint32_t taddr = tmem_base + uint32_t(acc * BN + c * 32) + (uint32_t(quad * 32) << 16);
-                LPI_TMEM_LD_X32(taddr, r);
-                tmem_ld_wait();
-                if (MODE == MODE_GEMM) {
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t r[32];
+                    const uint32_t taddr = tmem_base + uint32_t(acc * BN + c * 32) + (uint32_t(quad * 32) << 16);
+                    LPI_TMEM_LD_X32(taddr, r);
+                    tmem_ld_wait();
                     float4* stg = reinterpret_cast<float4*>(smem_gen + C::LIST_OFF) + (warp - 2) * 32 * 8;
 #pragma unroll
                     for (int j = 0; j < 8; ++j)          // own row, 16-byte chunk j -> swizzled slot
@@ -354,35 +406,15 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     __syncwarp();
                     epilogue_block<EPI>(p, stg, m0 + quad * 32, n0 + c * 32, lane);
                     __syncwarp();
-                } else {
-                    const int col0 = n0 + c * 32;
-                    if (col0 + 32 > p.N) {            // ragged gallery tail: rows past N were zero-filled by TMA
-#pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (col0 + j >= p.N) r[j] = 0xff800000u;   // -inf
-                    }
-                    float m = __uint_as_float(r[0]);
-#pragma unroll
-                    for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(r[j]));
-                    if (m > thr) {                    // rare after warm-up: ~k*ln(N/k) insertions per row in total
-                        const int k = p.k;
+                }
+            } else {
 #pragma unroll 1
-                        for (int j = 0; j < 32; ++j) {
-                            const float v = __uint_as_float(r[j]);
-                            if (v > thr) {            // strict: an equal score with a larger index never displaces
-                                int pos = cnt < k ? cnt : k - 1;
-                                while (pos > 0 && l_sc[(pos - 1) * BM + r_local] < v) {
-                                    l_sc[pos * BM + r_local] = l_sc[(pos - 1) * BM + r_local];
-                                    l_id[pos * BM + r_local] = l_id[(pos - 1) * BM + r_local];
-                                    --pos;
-                                }
-                                l_sc[pos * BM + r_local] = v;
-                                l_id[pos * BM + r_local] = int(p.gallery_offset) + col0 + j;
-                                if (cnt < k) ++cnt;
-                                if (cnt == k) thr = l_sc[(k - 1) * BM + r_local];
-                            }
-                        }
-                    }
+                for (int c = 0; c < BN / 64; ++c) {
+                    uint32_t r[64];
+                    const uint32_t taddr = tmem_base + uint32_t(acc * BN + c * 64) + (uint32_t(quad * 32) << 16);
+                    LPI_TMEM_LD_X64(taddr, r);
+                    tmem_ld_wait();
+                    topk_consume<64>(tk, r, n0 + c * 64, p.N, int(p.gallery_offset));
                 }
             }
             tc_fence_before();
@@ -396,8 +428,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     float* os = p.topk_scores + (size_t(chunk) * p.M + row) * p.k;
                     int* oi = p.topk_idx + (size_t(chunk) * p.M + row) * p.k;
                     for (int j = 0; j < p.k; ++j) {
-                        os[j] = j < cnt ? l_sc[j * BM + r_local] : -INFINITY;
-                        oi[j] = j < cnt ? l_id[j * BM + r_local] : 0x7fffffff;
+                        os[j] = j < tk.cnt ? tk.sc[j * BM + r_local] : -INFINITY;
+                        oi[j] = j < tk.cnt ? tk.id[j * BM + r_local] : 0x7fffffff;
                     }
                 }
             }
@@ -581,8 +613,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int r_local = quad * 32 + lane;
         int acc = 0;
         uint32_t acc_phase = 0;
-        float* l_sc = reinterpret_cast<float*>(smem_gen + C::LIST_OFF);
-        int* l_id = reinterpret_cast<int*>(smem_gen + C::LIST_OFF + BM * TOPK_MAX * 4);
+        TopkState tk{reinterpret_cast<float*>(smem_gen + C::LIST_OFF), reinterpret_cast<int*>(smem_gen + C::LIST_OFF + BM * TOPK_MAX * 4),
+                     r_local, p.k, 0, -INFINITY};
         const uint32_t tempty_leader0 = mapa_u32(tempty_bar(0), 0), tempty_leader1 = mapa_u32(tempty_bar(1), 0);
         for (int t = cluster_id; t < total; t += n_clusters) {
             const int mp = t % num_mp, second = t / num_mp;
@@ -591,19 +623,19 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             int n_begin, n_end;
             if (MODE == MODE_GEMM) { n_begin = second; n_end = second + 1; }
             else { n_begin = second * p.tiles_per_chunk; n_end = min(num_n, n_begin + p.tiles_per_chunk); }
-            float thr = -INFINITY;
-            int cnt = 0;
+            tk.thr = -INFINITY;
+            tk.cnt = 0;
             for (int nt = n_begin; nt < n_end; ++nt) {
                 const int n0 = nt * BN;
                 mbar_wait(tfull_bar(acc), acc_phase);
                 tc_fence_after();
+                if (MODE == MODE_GEMM) {
 #pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
-                    uint32_t r[32];
-                    const uint32_t taddr = tmem_base + uint32_t(acc * BN + c * 32) + (uint32_t(quad * 32) << 16);
-                    LPI_TMEM_LD_X32(taddr, r);
-                    tmem_ld_wait();
-                    if (MODE == MODE_GEMM) {
+                    for (int c = 0; c < BN / 32; ++c) {
+                        uint32_t r[32];
+                        const uint32_t taddr = tmem_base + uint32_t(acc * BN + c * 32) + (uint32_t(quad * 32) << 16);
+                        LPI_TMEM_LD_X32(taddr, r);
+                        tmem_ld_wait();
                         float4* stg = reinterpret_cast<float4*>(smem_gen + C::LIST_OFF) + (warp - 2) * 32 * 8;
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
@@ -612,35 +644,15 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         __syncwarp();
                         epilogue_block<EPI>(p, stg, m0 + quad * 32, n0 + c * 32, lane);
                         __syncwarp();
-                    } else {
-                        const int col0 = n0 + c * 32;
-                        if (col0 + 32 > p.N) {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (col0 + j >= p.N) r[j] = 0xff800000u;
-                        }
-                        float m = __uint_as_float(r[0]);
-#pragma unroll
-                        for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(r[j]));
-                        if (m > thr) {
-                            const int k = p.k;
+                    }
+                } else {
 #pragma unroll 1
-                            for (int j = 0; j < 32; ++j) {
-                                const float v = __uint_as_float(r[j]);
-                                if (v > thr) {
-                                    int pos = cnt < k ? cnt : k - 1;
-                                    while (pos > 0 && l_sc[(pos - 1) * BM + r_local] < v) {
-                                        l_sc[pos * BM + r_local] = l_sc[(pos - 1) * BM + r_local];
-                                        l_id[pos * BM + r_local] = l_id[(pos - 1) * BM + r_local];
-                                        --pos;
-                                    }
-                                    l_sc[pos * BM + r_local] = v;
-                                    l_id[pos * BM + r_local] = int(p.gallery_offset) + col0 + j;
-                                    if (cnt < k) ++cnt;
-                                    if (cnt == k) thr = l_sc[(k - 1) * BM + r_local];
-                                }
-                            }
-                        }
+                    for (int c = 0; c < BN / 64; ++c) {
+                        uint32_t r[64];
+                        const uint32_t taddr = tmem_base + uint32_t(acc * BN + c * 64) + (uint32_t(quad * 32) << 16);
+                        LPI_TMEM_LD_X64(taddr, r);
+                        tmem_ld_wait();
+                        topk_consume<64>(tk, r, n0 + c * 64, p.N, int(p.gallery_offset));
                     }
                 }
                 tc_fence_before();
@@ -652,8 +664,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 float* os = p.topk_scores + (size_t(second) * p.M + row) * p.k;
                 int* oi = p.topk_idx + (size_t(second) * p.M + row) * p.k;
                 for (int j = 0; j < p.k; ++j) {
-                    os[j] = j < cnt ? l_sc[j * BM + r_local] : -INFINITY;
-                    oi[j] = j < cnt ? l_id[j * BM + r_local] : 0x7fffffff;
+                    os[j] = j < tk.cnt ? tk.sc[j * BM + r_local] : -INFINITY;
+                    oi[j] = j < tk.cnt ? tk.id[j * BM + r_local] : 0x7fffffff;
                 }
             }
         }
@@ -816,14 +828,10 @@ static int gemm_entry(bool tf32, const void* A, const void* B, int M, int N, int
     if (!out) return set_error(LPI_ERR_ARG, "gemm: null output");
     int bn = tile_n;
     const int sms = num_sms();
-    if (bn == 0) {   // pick the tile width with the better wave efficiency
-        auto eff = [&](int b) {
-            if (N % b) return 0.0;
-            long tiles = long((M + BM - 1) / BM) * (N / b);
-            long waves = (tiles + sms - 1) / sms;
-            return double(tiles) / double(waves * sms);
-        };
-        bn = (N % 256 == 0 && eff(256) + 0.03 >= eff(128)) ? 256 : 128;   // prefer the wide tile unless quantisation hurts
+    if (bn == 0) {
+        // CTA-pair 256 x 256 tiles whenever N allows: they measured at or above the 1-CTA tiles on every encoder shape
+        // (profiles/r1_gemm_microbench_v2.txt); otherwise the narrow 1-CTA tile.
+        bn = (N % 256 == 0) ? 512 : 128;
     }
     const bool pair = (bn == 512);               // CTA-pair kernel: 256 x 256 tile over two SMs (cta_group::2)
     if (bn != 128 && bn != 256 && bn != 512) return set_error(LPI_ERR_ARG, "gemm: tile_n must be 0, 128, 256 or 512 (CTA pair)");
