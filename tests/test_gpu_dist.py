@@ -1,0 +1,84 @@
+"""-m gpu multi-GPU parity (needs >= 2 GPUs on the box, otherwise skipped): NCCL gallery-sharded search equals the single-GPU
+result bit for bit; the data-parallel training step (sharded batch, all-gathered features, all-reduced 5 284-float gradient)
+reproduces the single-process global-batch losses and gradients."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+
+def _scorer_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from lpi_b200 import ops, retrieval as R, synthetic as S
+
+        ng, nq = 200_000, 3000
+        lo, hi = R.shard_bounds(ng, world, rank, align=256)
+        shard, q, gt = S.make_gallery_shard(ng, lo, hi, nq, 512, device=f"cuda:{rank}")
+        sc, ix = R.search_topk(q, shard, 10, "bf16", lo, dist.group.WORLD)
+        if rank == 0:
+            full, q2, _ = S.make_gallery_shard(ng, 0, ng, nq, 512, device="cuda:0")
+            assert torch.equal(q, q2) and torch.equal(full[lo:hi], shard)          # sharding-independent workload
+            s1, i1 = ops.sim_topk(q2, full, 10)
+            out.put(("scorer", bool(torch.equal(ix, i1) and torch.equal(sc, s1))))
+    finally:
+        dist.destroy_process_group()
+
+
+def _train_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from lpi_b200 import lpi_step, ops, synthetic as S
+        from lpi_b200.engine import TextEngine, VisionEngine
+
+        sd = S.make_clip_state_dict(0)
+        vision, text = VisionEngine(sd, dev), TextEngine(sd, dev)
+        B = 8
+        images, tokens = S.make_images(B, 3).to(dev), S.make_tokens(B, 3).to(dev)
+        fac = {k: v.to(dev) for k, v in S.make_prompt_factors(2).items()}
+        prev = [lpi_step.reconstruct({k: v.to(dev) for k, v in S.make_prompt_factors(0).items()})]
+        sim = np.loadtxt(os.path.join(os.path.dirname(os.path.abspath(ops.__file__)), "MID", "task_sim_matrix.txt"))
+        tgt = torch.tensor((sim[:2, :2] > 0.4).astype(np.int32), device=dev)
+        b = B // world
+        r = lpi_step.train_step(vision, text, fac, images[rank * b:(rank + 1) * b], tokens[rank * b:(rank + 1) * b], 1 / 0.07, prev, tgt,
+                                group=dist.group.WORLD)
+        if rank == 0:
+            ref = lpi_step.train_step(vision, text, fac, images, tokens, 1 / 0.07, prev, tgt)
+            ok = True
+            for k in ref["losses"]:
+                ok &= abs(float(r["losses"][k]) - float(ref["losses"][k])) < 1e-4 * max(1.0, abs(float(ref["losses"][k])))
+            worst = 0.0
+            for k in lpi_step.FACTOR_NAMES:
+                worst = max(worst, float((r["grads"][k] - ref["grads"][k]).norm() / ref["grads"][k].norm()))
+            out.put(("train", bool(ok and worst < 2e-3), worst))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("worker", [_scorer_worker, _train_worker])
+def test_two_gpu_parity(worker):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 29600 + os.getpid() % 2000
+    procs = [ctx.Process(target=worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = out.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert res[1], res
