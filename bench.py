@@ -335,9 +335,65 @@ def run_b200(args):
                              "flops_per_launch": flops,
                              "algorithmic_bytes_per_launch": (hi - lo) * DIM * 2 + nq * DIM * 2 + nq * TOPK * 8}}
         line.update(line_extra)
+    train = None
+    if not args.skip_train:
+        del shard, g_dev, g_host                     # free the gallery before building the towers
+        torch.cuda.empty_cache()
+        try:
+            train = train_leg(dev, world, rank, group, max(3, min(args.steps, 10)), 3)
+        except Exception as e:                       # the secondary leg must never take the headline line down
+            train = {"error": repr(e)[:300]}
+    if rank == 0:
+        line["train"] = train
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def train_leg(dev, world, rank, group, steps, warmup, batch_per_gpu=64):
+    """Secondary metric of BASELINE.json ('prompted-CLIP train pairs/sec', configs[2]): COCO-shaped LPI training step, batch 64 per
+    GPU, data-parallel over the ranks (global InfoNCE over all-gathered features, all-reduced prompt gradient), SGD step included."""
+    import torch
+    import torch.distributed as dist
+    from lpi_b200 import lpi_step, ops, synthetic as S
+    from lpi_b200.engine import TextEngine, VisionEngine
+
+    sd = S.make_clip_state_dict(0)
+    vision, text = VisionEngine(sd, dev), TextEngine(sd, dev)
+    fac = {k: v.to(dev) for k, v in S.make_prompt_factors(0).items()}
+    opt = lpi_step.PromptSGD(fac, 0.05)
+    images = S.make_images(batch_per_gpu, rank).to(dev)
+    tokens = S.make_tokens(batch_per_gpu, rank).to(dev)
+
+    def step():
+        r = lpi_step.train_step(vision, text, fac, images, tokens, 1 / 0.07, group=group)
+        opt.step(r["grads"])
+        return r
+
+    for _ in range(warmup):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    n0 = ops.KERNEL_LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        r = step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms)
+    gb = batch_per_gpu * world
+    return {"metric": "prompted_clip_train_pairs_per_sec", "value": gb / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms,
+            "global_batch": gb, "parallelism": f"dp{world}", "launches_per_step": (ops.KERNEL_LAUNCHES - n0) / steps,
+            "algorithmic_tflops": gb * 89.7e9 / (ms * 1e-3) / 1e12, "loss": float(r["losses"]["base_loss"]),
+            "precision": "vision bf16 / text tf32 operands, fp32 accumulate", "workload": "BASELINE.json configs[2]: ViT-B/16 + 12-layer text, "
+            "224x224 synthetic images, 77-token captions, random init, fwd + 3 losses + dgrad to 5 284 prompt scalars + SGD"}
 
 
 def main():
@@ -349,6 +405,7 @@ def main():
     ap.add_argument("--gallery", type=int, default=5_000_000)
     ap.add_argument("--queries", type=int, default=25_000)
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs: no cpu_baseline / parity leg")
+    ap.add_argument("--skip-train", action="store_true", help="skip the secondary train pairs/s leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

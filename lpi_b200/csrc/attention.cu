@@ -58,11 +58,13 @@ __device__ __forceinline__ void load_a_frags(uint32_t tile, int r0, uint32_t (&a
 }
 
 // acc[8][4] (16 x 64) = A(16 x 64) . T[rows t0..t0+63][0..63]^T   (T row-major [n][k]: "K pattern")
-__device__ __forceinline__ void mma_a_tT(float (&acc)[8][4], const uint32_t (&a)[4][4], uint32_t tile, int t0) {
+// `steps` (1..4, warp-uniform) = number of 16-row groups of T that hold valid rows; the rest are skipped (their accumulators stay 0)
+__device__ __forceinline__ void mma_a_tT(float (&acc)[8][4], const uint32_t (&a)[4][4], uint32_t tile, int t0, int steps = 4) {
     const int lane = threadIdx.x & 31;
     const int m = lane >> 3, r = lane & 7;
 #pragma unroll
     for (int np = 0; np < 4; ++np) {            // pairs of 8-wide n tiles
+        if (np >= steps) break;
         const int row = t0 + np * 16 + (m >> 1) * 8 + r;
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
@@ -75,11 +77,12 @@ __device__ __forceinline__ void mma_a_tT(float (&acc)[8][4], const uint32_t (&a)
 }
 
 // acc[8][4] (16 x 64) += P(16 x 64, bf16 A fragments p[4][4]) . T[rows t0..t0+63][0..63]   (T row-major [k][n]: "V pattern")
-__device__ __forceinline__ void mma_p_t(float (&acc)[8][4], const uint32_t (&p)[4][4], uint32_t tile, int t0) {
+__device__ __forceinline__ void mma_p_t(float (&acc)[8][4], const uint32_t (&p)[4][4], uint32_t tile, int t0, int steps = 4) {
     const int lane = threadIdx.x & 31;
     const int m = lane >> 3, r = lane & 7;
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {            // 16 rows of T per k-step
+        if (ks >= steps) break;
         const int row = t0 + ks * 16 + (m & 1) * 8 + r;
 #pragma unroll
         for (int np = 0; np < 4; ++np) {
@@ -160,6 +163,7 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (q0 + warp * 16 >= L) return;                        // this warp's 16 rows are all padding (L = 213: 2 of 16 warps)
     const int r_lo = q0 + warp * 16 + (lane >> 2);          // this thread's two rows: r_lo, r_lo + 8
     uint32_t qa[4][4];
     load_a_frags(sQ, warp * 16, qa);
@@ -172,7 +176,8 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
         float s[8][4];
 #pragma unroll
         for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
-        mma_a_tT(s, qa, sK, kb * 64);
+        const int steps = min(4, (kmax - kb * 64 + 15) >> 4);   // 16-key groups with at least one valid key
+        mma_a_tT(s, qa, sK, kb * 64, steps);
         float bm[2] = {-INFINITY, -INFINITY};
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt)
@@ -206,7 +211,7 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
         }
         uint32_t pa[4][4];
         acc_to_a(s, pa);
-        mma_p_t(o, pa, sV, kb * 64);
+        mma_p_t(o, pa, sV, kb * 64, steps);
     }
     l[0] = quad_sum(l[0]);
     l[1] = quad_sum(l[1]);
@@ -262,6 +267,7 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (q0 + warp * 16 >= L) return;
     const int r_lo = q0 + warp * 16 + (lane >> 2);
     uint32_t qa[4][4], da[4][4];
     load_a_frags(sQ, warp * 16, qa);
@@ -286,8 +292,9 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
             s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
             dpv[i][0] = dpv[i][1] = dpv[i][2] = dpv[i][3] = 0.f;
         }
-        mma_a_tT(s, qa, sK, kb * 64);
-        mma_a_tT(dpv, da, sV, kb * 64);
+        const int steps = min(4, (kmax - kb * 64 + 15) >> 4);
+        mma_a_tT(s, qa, sK, kb * 64, steps);
+        mma_a_tT(dpv, da, sV, kb * 64, steps);
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
@@ -300,7 +307,7 @@ attn_bwd_dq_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* _
             }
         uint32_t dsa[4][4];
         acc_to_a(s, dsa);
-        mma_p_t(dq, dsa, sK, kb * 64);
+        mma_p_t(dq, dsa, sK, kb * 64, steps);
     }
     if (dqkv_f32) store_tile_f32(dq, dqkv_f32 + long(b) * L * ld + h * DH, ld, q0 + warp * 16, L, scale);
     else store_tile_bf16(dq, dqkv + long(b) * L * ld + h * DH, ld, q0 + warp * 16, L, scale);
@@ -336,6 +343,7 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (k0 + warp * 16 >= L) return;                        // all 16 keys of this warp are padding
     const int j_lo = k0 + warp * 16 + (lane >> 2);          // this thread's two keys: j_lo, j_lo + 8
     uint32_t ka[4][4], va[4][4];
     load_a_frags(sK, warp * 16, ka);
@@ -353,8 +361,9 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
             st[i][0] = st[i][1] = st[i][2] = st[i][3] = 0.f;
             dpt[i][0] = dpt[i][1] = dpt[i][2] = dpt[i][3] = 0.f;
         }
-        mma_a_tT(st, ka, sQ, qb * 64);          // S^T tile: 16 keys x 64 queries
-        mma_a_tT(dpt, va, sdO, qb * 64);        // dP^T tile
+        const int steps = min(4, (L - q_begin - qb * 64 + 15) >> 4);    // 16-query groups with at least one valid query
+        mma_a_tT(st, ka, sQ, qb * 64, steps);   // S^T tile: 16 keys x 64 queries
+        mma_a_tT(dpt, va, sdO, qb * 64, steps); // dP^T tile
         uint32_t pa[4][4], dsa[4][4];
 #pragma unroll
         for (int nt = 0; nt < 8; ++nt)
@@ -370,8 +379,8 @@ attn_bwd_dkv_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* 
             }
         acc_to_a(st, pa);
         acc_to_a(dpt, dsa);
-        mma_p_t(dv, pa, sdO, qb * 64);          // dV += P^T dO
-        mma_p_t(dk, dsa, sQ, qb * 64);          // dK += dS^T Q
+        mma_p_t(dv, pa, sdO, qb * 64, steps);   // dV += P^T dO
+        mma_p_t(dk, dsa, sQ, qb * 64, steps);   // dK += dS^T Q
     }
     if (dqkv_f32) {
         float* dbase = dqkv_f32 + long(b) * L * ld + h * DH;

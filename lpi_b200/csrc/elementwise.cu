@@ -272,11 +272,14 @@ head_fwd_kernel(const float* __restrict__ x, const int* __restrict__ row_idx, co
     float acc[HB];
 #pragma unroll
     for (int h = 0; h < HB; ++h) acc[h] = 0.f;
-#pragma unroll 8
-    for (int k = 0; k < D; ++k) {
-        const float w = proj[long(k) * E + e];
+    for (int k0 = 0; k0 < D; k0 += 16) {             // 16 independent weight loads in flight per thread (D % 16 == 0)
+        float w[16];
 #pragma unroll
-        for (int h = 0; h < HB; ++h) acc[h] = fmaf(y[h * D + k], w, acc[h]);
+        for (int i = 0; i < 16; ++i) w[i] = __ldg(proj + long(k0 + i) * E + e);
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+#pragma unroll
+            for (int h = 0; h < HB; ++h) acc[h] = fmaf(y[h * D + k0 + i], w[i], acc[h]);
     }
 #pragma unroll
     for (int h = 0; h < HB; ++h)
@@ -323,11 +326,18 @@ head_bwd_kernel(const float* __restrict__ dfeat, const float* __restrict__ dz_di
         dz[e] = v;
     }
     __syncthreads();
-    for (int k = warp; k < D; k += 8) {              // dy[k] = sum_e dz[e] proj[k, e]  (warp per k, coalesced over e)
-        float s = 0.f;
-        for (int e = lane; e < E; e += 32) s = fmaf(dz[e], proj[long(k) * E + e], s);
-        s = warp_sum(s);
-        if (lane == 0) dy[k] = s;
+    for (int k = warp * 4; k < D; k += 32) {         // dy[k] = sum_e dz[e] proj[k, e]: a warp takes 4 rows of proj at a time
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int e = lane; e < E; e += 32) {
+            const float d = dz[e];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) s4[i] = fmaf(d, __ldg(proj + long(k + i) * E + e), s4[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float v = warp_sum(s4[i]);
+            if (lane == 0) dy[k + i] = v;
+        }
     }
     __syncthreads();
     // LN backward over the row (block-wide)

@@ -27,5 +27,25 @@ def run() -> None:
     ref = a.float() @ w.float().t() + b
     err = (out.float() - ref).abs().max().item()
     assert err < 2e-2 * ref.abs().max().item(), f"gemm error {err}"
+    # 3. one LPI training step (both towers fwd, 3 losses, backward to the prompt factors) vs the fixture produced by the REAL reference
+    import os
+
+    from . import lpi_step
+    from .engine import TextEngine, VisionEngine
+
+    gold = torch.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "model_b4_seed0.pt"),
+                      weights_only=False)
+    sd = S.make_clip_state_dict(0)
+    vision, text = VisionEngine(sd, dev), TextEngine(sd, dev)
+    fac = {k: v.to(dev) for k, v in S.make_prompt_factors(0).items()}
+    r = lpi_step.train_step(vision, text, fac, S.make_images(4, 0).to(dev), gold["tokens"].to(dev), 1 / 0.07)
+    want = gold["step_task1"]
+    rel = lambda a, b: float((a.double().cpu() - b.double()).norm() / b.double().norm())
+    assert rel(r["img_f"], want["img_f"]) < 1e-2 and rel(r["txt_f"], want["txt_f"]) < 1e-2, "feature parity"
+    for k2, v2 in want["losses"].items():
+        assert abs(float(r["losses"][k2]) - v2) < 1e-2 * max(abs(v2), 1e-3), f"loss {k2}"
+    worst = max(rel(r["grads"][k2], want["grads"][k2]) for k2 in O.FACTOR_NAMES)
+    assert worst < 2e-2, f"prompt-gradient parity {worst}"
     torch.cuda.synchronize()
+    print("train step ok: base_loss %.4f, worst prompt-grad rel err %.2e" % (float(r["losses"]["base_loss"]), worst))
     print("smoke ok: Recall@K bit-exact vs oracle; gemm max err %.3e; lpi kernels launched: %d" % (err, ops.KERNEL_LAUNCHES))
