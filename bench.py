@@ -68,7 +68,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", self.sel, f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
         except Exception:
@@ -215,6 +215,8 @@ def run_b200(args):
     barrier()
     launches = ops.KERNEL_LAUNCHES - launches0
     clocks = sampler.stop() if sampler else None
+    if clocks is not None:
+        clocks["sampled_over"] = "device-resident timed steps"
     ms_total = torch.tensor([t0.elapsed_time(t1)], device=dev, dtype=torch.float64)
     kern_ms = torch.tensor([sum(a.elapsed_time(b) for a, b in kern_events) / len(kern_events)], device=dev, dtype=torch.float64)
     if world > 1:
@@ -263,6 +265,10 @@ def run_b200(args):
         e2e_step()
     barrier()
     e2e_steps = max(1, min(args.steps, 5))
+    sampler2 = None
+    if rank == 0 and clocks is not None and (clocks.get("samples") or 0) < 3:     # short timed region (many GPUs): sample the e2e steps too
+        sampler2 = ClockSampler(local)
+        sampler2.start()
     w0 = time.perf_counter()
     t0.record()
     for _ in range(e2e_steps):
@@ -274,6 +280,11 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_ms = float(e2e_ms) / e2e_steps
+    if sampler2 is not None:
+        c2 = sampler2.stop()
+        if (c2.get("samples") or 0) > (clocks.get("samples") or 0):
+            clocks = c2
+            clocks["sampled_over"] = "e2e timed steps (the device-resident region was shorter than 3 samples)"
     e2e_counts = out_counts.clone()
     h2d = q_host.numel() * 2 + g_host.numel() * 2
     d2h = out_ix.numel() * 4 + out_counts.numel() * 4
