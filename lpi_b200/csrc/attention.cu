@@ -417,6 +417,7 @@ static int attn_check(int B, int L, int H) {
 
 extern "C" int lpi_attn_fwd(const void* qkv, void* out, float* out_f32, float* lse2, int B, int L, int H, int causal, void* stream) {
     if (int rc = attn_check(B, L, H)) return rc;
+    if (attn_tc_enabled(L)) return attn_fwd_tc(qkv, out, out_f32, lse2, B, L, H, causal, static_cast<cudaStream_t>(stream));
     const float scale_log2 = 0.125f * 1.4426950408889634f;      // 1/sqrt(64) * log2(e)
     const dim3 grid((L + QB - 1) / QB, H, B);
     const int smem = attn_smem_fwd(L);
@@ -445,6 +446,7 @@ extern "C" int lpi_attn_bwd(const void* qkv, const void* out, const void* d_out,
     auto dq = static_cast<__nv_bfloat16*>(dqkv);
     const long rows = long(B) * L;
     attn_delta_kernel<<<unsigned((rows * 32 + 255) / 256), 256, 0, st>>>(o, d_o, delta_ws, B, L, H);
+    if (attn_tc_enabled(L)) return attn_bwd_tc(qkv, d_out, lse2, delta_ws, dqkv, dqkv_f32, B, L, H, causal, st);
     const dim3 grid((L + QB - 1) / QB, H, B);
     if (causal) {
         if (int rc = set_smem(attn_bwd_dq_kernel<true>, attn_smem_dq(L))) return rc;
