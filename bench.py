@@ -403,7 +403,7 @@ def train_leg(dev, world, rank, group, steps, warmup, batch_per_gpu=64):
     return {"metric": "prompted_clip_train_pairs_per_sec", "value": gb / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms,
             "global_batch": gb, "parallelism": f"dp{world}", "launches_per_step": (ops.KERNEL_LAUNCHES - n0) / steps,
             "algorithmic_tflops": gb * 89.7e9 / (ms * 1e-3) / 1e12, "loss": float(r["losses"]["base_loss"]),
-            "precision": "vision bf16 / text tf32 operands, fp32 accumulate", "workload": "BASELINE.json configs[2]: ViT-B/16 + 12-layer text, "
+            "precision": "vision bf16 / text fp16 operands, fp32 accumulate", "workload": "BASELINE.json configs[2]: ViT-B/16 + 12-layer text, "
             "224x224 synthetic images, 77-token captions, random init, fwd + 3 losses + dgrad to 5 284 prompt scalars + SGD"}
 
 

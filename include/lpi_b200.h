@@ -56,6 +56,12 @@ int lpi_gemm_bf16(const void* A, const void* B, int M, int N, int K, int epi, co
  * A [M,K] fp32, B [N,K] fp32, K % 32 == 0.  Epilogues: BIAS_BF16, BIAS_RESID_F32, F32, BF16, BIAS_GELU_F32, DGELU_F32. */
 int lpi_gemm_tf32(const void* A, const void* B, int M, int N, int K, int epi, const void* bias_f32, const void* resid_f32,
                   void* out, void* out2, const void* aux, int ldo, int tile_n, void* stream);
+/* Same pipeline with fp16 operands (tcgen05.mma kind::f16, fp16 inputs): the 10-bit mantissa of TF32 at the full bf16 rate and half
+ * the operand bytes -- the reference itself runs its CLIP weights in fp16 on the GPU (models/clip/model.py:394-415,522).  Every
+ * "bf16" output / out2 / aux of the epilogue table is fp16 here.  N % 256 == 0 (CTA-pair tiles), K % 64 == 0.
+ * Epilogues: BIAS_BF16, BIAS_GELU_BF16, BIAS_RESID_F32, F32, ACC_F32, DGELU_BF16, BF16, BIAS_F32. */
+int lpi_gemm_f16(const void* A, const void* B, int M, int N, int K, int epi, const void* bias_f32, const void* resid_f32,
+                 void* out, void* out2, const void* aux_f16, int ldo, int tile_n, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Retrieval scorer: similarity GEMM with the top-k kept in the epilogue (score matrix never written).
@@ -102,6 +108,11 @@ int lpi_attn_fwd(const void* qkv, void* out, float* out_f32 /* optional fp32 cop
 int lpi_attn_bwd(const void* qkv, const void* out, const void* d_out, const float* lse2, float* delta_ws, void* dqkv,
                  float* dqkv_f32 /* if non-NULL the gradient is written here in fp32 instead of dqkv */, int B, int L, int H,
                  int causal, void* stream);
+/* fp16 storage for qkv / out / d_out / dqkv (and P, dS inside the kernels); L <= 256.  The backward is linear in d_out, so a
+ * caller that scales d_out by a power of two (fp16 gradient scaling) gets dqkv scaled by the same factor. */
+int lpi_attn_fwd_f16(const void* qkv, void* out, float* lse2, int B, int L, int H, int causal, void* stream);
+int lpi_attn_bwd_f16(const void* qkv, const void* out, const void* d_out, const float* lse2, float* delta_ws, void* dqkv, int B, int L,
+                     int H, int causal, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * LayerNorm in fp32 (models/clip/model.py:154-160; eps inside the sqrt, biased variance).
@@ -113,6 +124,13 @@ int lpi_layernorm_fwd(const float* x, const float* gamma, const float* beta, flo
                       float eps, void* stream);
 int lpi_layernorm_bwd(const float* dy, const float* x, const float* gamma, float* g, void* g_bf16, long long M, int D, float eps,
                       int accumulate, void* stream);
+/* fp16 shadows for the fp16 GEMM path.  The fp16 gradient stream is carried multiplied by grad_scale (a power of two, so the
+ * scaling is exact) to keep small gradients inside fp16's normal range: dy_scaled = grad_scale * dy, g stays true-scale fp32,
+ * g_f16 = fp16(grad_scale * g). */
+int lpi_layernorm_fwd_f16(const float* x, const float* gamma, const float* beta, float* out_f32, void* out_f16, long long M, int D,
+                          float eps, void* stream);
+int lpi_layernorm_bwd_f16(const float* dy_scaled, const float* x, const float* gamma, float* g, void* g_f16, long long M, int D,
+                          float eps, int accumulate, float grad_scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Vision front end (VisionTransformer.forward, models/clip/model.py:227-250).
@@ -154,6 +172,9 @@ int lpi_head_fwd(const float* x, const int* row_idx, const float* ln_gamma, cons
                  float* feat_out, int B, int D, int E, float eps, void* stream);
 int lpi_head_bwd(const float* dfeat, const float* dz_direct, const float* z, const float* x, const int* row_idx, const float* ln_gamma,
                  const float* proj, float* g, void* g_bf16, int B, int D, int E, float eps, void* stream);
+/* same with g_f16 = fp16(grad_scale * g) as the shadow (fp16 gradient path, see lpi_layernorm_bwd_f16) */
+int lpi_head_bwd_f16(const float* dfeat, const float* dz_direct, const float* z, const float* x, const int* row_idx, const float* ln_gamma,
+                     const float* proj, float* g, void* g_f16, float grad_scale, int B, int D, int E, float eps, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * DecomposedPrompt (models/prompts/prompts.py:38-57): Y[l,p,d] = mean_k dim1[l,k] dim2[p,k] dim3[d,k], dim1 shared by both

@@ -119,7 +119,7 @@ class CLIP(nn.Module):
         self.text_projection = nn.Parameter(torch.empty(transformer_width, embed_dim))
         self.logit_scale = nn.Parameter(torch.ones([]) * np.log(1 / 0.07))
         self.inject_layers: Tuple[int, ...] = ()
-        self.text_precision = "tf32"          # 'tf32' (parity default) or 'bf16' -- see engine.TextEngine
+        self.text_precision = "fp16"          # 'fp16' (default), 'tf32' or 'bf16' -- see engine.TextEngine
         self._text_engine: Optional[TextEngine] = None
         self.initialize_parameters()
 

@@ -11,6 +11,7 @@
 // log-sum-exp (log2 domain) so the backward recomputes P exactly as the forward saw it.
 // Sequences are short (L <= 256) and attention is ~4% of the tower FLOPs; whole K/V
 // of one head live in shared memory, so there is no K/V streaming pipeline to manage.
+#include <cuda_fp16.h>
 #include "ptx.cuh"
 #include "lpi_internal.h"
 
@@ -229,16 +230,19 @@ attn_fwd_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict
 
 // ------------------------------------------------------------------------------------------------ backward
 // delta[b,h,l] = sum_d dO[b,l,h,d] * O[b,l,h,d]   (one warp per token row, all heads)
+template <bool F16>
 __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o, float* __restrict__ delta,
                                   int B, int L, int H) {
     const long row = (long(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     if (row >= long(B) * L) return;
     const int lane = threadIdx.x & 31;
     const int b = int(row / L), l = int(row - long(b) * L);
-    const __nv_bfloat162* po = reinterpret_cast<const __nv_bfloat162*>(o + row * H * DH);
-    const __nv_bfloat162* pd = reinterpret_cast<const __nv_bfloat162*>(d_o + row * H * DH);
+    const uint32_t* po = reinterpret_cast<const uint32_t*>(o + row * H * DH);
+    const uint32_t* pd = reinterpret_cast<const uint32_t*>(d_o + row * H * DH);
     for (int h = 0; h < H; ++h) {
-        const float2 a = __bfloat1622float2(po[h * 32 + lane]), c = __bfloat1622float2(pd[h * 32 + lane]);
+        const uint32_t wa = po[h * 32 + lane], wc = pd[h * 32 + lane];
+        const float2 a = F16 ? __half22float2(*reinterpret_cast<const __half2*>(&wa)) : __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wa));
+        const float2 c = F16 ? __half22float2(*reinterpret_cast<const __half2*>(&wc)) : __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&wc));
         const float v = warp_sum(a.x * c.x + a.y * c.y);
         if (lane == 0) delta[(long(b) * H + h) * L + l] = v;
     }
@@ -417,7 +421,7 @@ static int attn_check(int B, int L, int H) {
 
 extern "C" int lpi_attn_fwd(const void* qkv, void* out, float* out_f32, float* lse2, int B, int L, int H, int causal, void* stream) {
     if (int rc = attn_check(B, L, H)) return rc;
-    if (attn_tc_enabled(L)) return attn_fwd_tc(qkv, out, out_f32, lse2, B, L, H, causal, static_cast<cudaStream_t>(stream));
+    if (attn_tc_enabled(L)) return attn_fwd_tc(qkv, out, out_f32, lse2, B, L, H, causal, false, static_cast<cudaStream_t>(stream));
     const float scale_log2 = 0.125f * 1.4426950408889634f;      // 1/sqrt(64) * log2(e)
     const dim3 grid((L + QB - 1) / QB, H, B);
     const int smem = attn_smem_fwd(L);
@@ -445,8 +449,8 @@ extern "C" int lpi_attn_bwd(const void* qkv, const void* out, const void* d_out,
     auto d_o = static_cast<const __nv_bfloat16*>(d_out);
     auto dq = static_cast<__nv_bfloat16*>(dqkv);
     const long rows = long(B) * L;
-    attn_delta_kernel<<<unsigned((rows * 32 + 255) / 256), 256, 0, st>>>(o, d_o, delta_ws, B, L, H);
-    if (attn_tc_enabled(L)) return attn_bwd_tc(qkv, d_out, lse2, delta_ws, dqkv, dqkv_f32, B, L, H, causal, st);
+    attn_delta_kernel<false><<<unsigned((rows * 32 + 255) / 256), 256, 0, st>>>(o, d_o, delta_ws, B, L, H);
+    if (attn_tc_enabled(L)) return attn_bwd_tc(qkv, d_out, lse2, delta_ws, dqkv, dqkv_f32, B, L, H, causal, false, st);
     const dim3 grid((L + QB - 1) / QB, H, B);
     if (causal) {
         if (int rc = set_smem(attn_bwd_dq_kernel<true>, attn_smem_dq(L))) return rc;
@@ -460,4 +464,23 @@ extern "C" int lpi_attn_bwd(const void* qkv, const void* out, const void* d_out,
         attn_bwd_dkv_kernel<false><<<grid, ATT_THREADS, attn_smem_dkv(L), st>>>(q, d_o, lse2, delta_ws, dq, dqkv_f32, L, H, scale, scale_log2);
     }
     return check_launch("attn_bwd");
+}
+
+// fp16 storage (q / k / v / P / dS / outputs), tcgen05 kernels only (L <= 256): the text tower's precision class
+extern "C" int lpi_attn_fwd_f16(const void* qkv, void* out, float* lse2, int B, int L, int H, int causal, void* stream) {
+    if (int rc = attn_check(B, L, H)) return rc;
+    if (L > 256) return set_error(LPI_ERR_UNSUPPORTED, "attn_fwd_f16: L=%d > 256", L);
+    return attn_fwd_tc(qkv, out, nullptr, lse2, B, L, H, causal, true, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int lpi_attn_bwd_f16(const void* qkv, const void* out, const void* d_out, const float* lse2, float* delta_ws, void* dqkv, int B, int L,
+                                int H, int causal, void* stream) {
+    if (int rc = attn_check(B, L, H)) return rc;
+    if (L > 256) return set_error(LPI_ERR_UNSUPPORTED, "attn_bwd_f16: L=%d > 256", L);
+    if (!dqkv) return set_error(LPI_ERR_ARG, "attn_bwd_f16: no output");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long rows = long(B) * L;
+    attn_delta_kernel<true><<<unsigned((rows * 32 + 255) / 256), 256, 0, st>>>(static_cast<const __nv_bfloat16*>(out),
+                                                                               static_cast<const __nv_bfloat16*>(d_out), delta_ws, B, L, H);
+    return attn_bwd_tc(qkv, d_out, lse2, delta_ws, dqkv, nullptr, B, L, H, causal, true, st);
 }

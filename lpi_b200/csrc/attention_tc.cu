@@ -17,6 +17,7 @@
 //     warps : O / rowsum -> bf16 -> per-warp smem transpose -> 16-byte coalesced global stores; log2-domain LSE per row
 //
 //   backward, one CTA per (head, sample): see attn_bwd_tc_kernel below.
+#include <cuda_fp16.h>
 #include "ptx.cuh"
 #include "lpi_internal.h"
 #include <stdlib.h>
@@ -52,7 +53,17 @@ __device__ __forceinline__ uint64_t make_desc_mnmajor_sw128(uint32_t saddr, uint
     return make_smem_desc(saddr, lbo_bytes, 1024, 2);
 }
 // runtime-N instruction descriptor (make_idesc is constexpr but N is only known at launch)
-__device__ __forceinline__ uint32_t idesc_bf16(int M, int N, int a_mn, int b_mn) { return make_idesc(kFmtBF16, M, N, a_mn, b_mn); }
+template <bool F16>
+__device__ __forceinline__ uint32_t idesc_h(int M, int N, int a_mn, int b_mn) { return make_idesc(F16 ? kFmtF16 : kFmtBF16, M, N, a_mn, b_mn); }
+// 16-bit storage type of q / k / v / P / dS / outputs: bf16 (vision tower) or fp16 (F16: text tower, 10-bit mantissa)
+template <bool F16>
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+    if (F16) {
+        const __half2 v = __floats2half2_rn(lo, hi);
+        return *reinterpret_cast<const uint32_t*>(&v);
+    }
+    return pack_bf16x2(lo, hi);
+}
 
 // Debug timeline: with a trace buffer installed (lpi_debug_attn_trace), the first and the last CTA of the grid record clock64()
 // at their pipeline events; 64 slots per CTA.  Null in production: one predictable branch per event.
@@ -79,7 +90,7 @@ constexpr int FWD_THREADS = 160;
 constexpr int FWD_BAR_OFF = 6 * TC_TILE;                    // Q | K (2 tiles) | V (2 tiles) | P block 3
 constexpr int FWD_SMEM = FWD_BAR_OFF + 128 + 1024;          // + barriers + 1024-byte alignment slack
 
-template <bool CAUSAL>
+template <bool CAUSAL, bool F16>
 __global__ void __launch_bounds__(FWD_THREADS, 2)
 attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const AttnFwdArgs p) {
     extern __shared__ uint8_t smem_raw[];
@@ -132,14 +143,14 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             mbar_wait(bar_qk, 0);
             LPI_TRACE(p, 2);
             tc_fence_after();
-            const uint32_t idesc_s = idesc_bf16(TC_BM, kpad, 0, 0);
+            const uint32_t idesc_s = idesc_h<F16>(TC_BM, kpad, 0, 0);
             const uint64_t dq = make_desc_kmajor_sw128(sQ), dk = make_desc_kmajor_sw128(sK);
 #pragma unroll
             for (int k = 0; k < 4; ++k) umma_f16_ss(tmem, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
             umma_commit(bar_s);
             mbar_wait(bar_v, 0);
             LPI_TRACE(p, 3);
-            const uint32_t idesc_o = idesc_bf16(TC_BM, 64, 0, 1);       // B = V is MN-major
+            const uint32_t idesc_o = idesc_h<F16>(TC_BM, 64, 0, 1);       // B = V is MN-major
             const int n_blk = (kpad + 63) >> 6;
             for (int c = 0; c < n_blk; ++c) {
                 mbar_wait(bar_p(c), 0);
@@ -194,7 +205,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                         const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * j]), sc, -m2));
                         const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * j + 1]), sc, -m2));
                         sum += p0 + p1;
-                        pk[j] = pack_bf16x2(p0, p1);
+                        pk[j] = pack_h2<F16>(p0, p1);
                     }
                 } else {
 #pragma unroll
@@ -204,7 +215,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                         if (sb * 32 + 2 * j >= lim) p0 = 0.f;
                         if (sb * 32 + 2 * j + 1 >= lim) p1 = 0.f;
                         sum += p0 + p1;
-                        pk[j] = pack_bf16x2(p0, p1);
+                        pk[j] = pack_h2<F16>(p0, p1);
                     }
                 }
             } else {
@@ -245,7 +256,7 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             uint32_t w[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e)
-                w[e] = pack_bf16x2(__uint_as_float(o[8 * q + 2 * e]) * inv, __uint_as_float(o[8 * q + 2 * e + 1]) * inv);
+                w[e] = pack_h2<F16>(__uint_as_float(o[8 * q + 2 * e]) * inv, __uint_as_float(o[8 * q + 2 * e + 1]) * inv);
             st_shared_v4(stg + uint32_t(r) * 128u + (uint32_t(q ^ (r & 7)) << 4), w[0], w[1], w[2], w[3]);
         }
         __syncwarp();
@@ -335,17 +346,18 @@ __device__ __forceinline__ void store_row_f32(float* dst, const uint32_t (&v)[N]
                             __uint_as_float(v[4 * q + 3]) * mul);
 }
 // 32 fp32 values of one row -> bf16 -> chunks [chunk0, chunk0 + 4) of the row's 128-byte line in a SWIZZLE_128B staging tile
-__device__ __forceinline__ void stage_row32_bf16(uint32_t tile, int row, int chunk0, const uint32_t (&v)[32], float mul) {
+template <bool F16>
+__device__ __forceinline__ void stage_row32_h(uint32_t tile, int row, int chunk0, const uint32_t (&v)[32], float mul) {
 #pragma unroll
     for (int q = 0; q < 4; ++q)
         st_shared_v4(tile + uint32_t(row) * 128u + (uint32_t((chunk0 + q) ^ (row & 7)) << 4),
-                     pack_bf16x2(__uint_as_float(v[8 * q]) * mul, __uint_as_float(v[8 * q + 1]) * mul),
-                     pack_bf16x2(__uint_as_float(v[8 * q + 2]) * mul, __uint_as_float(v[8 * q + 3]) * mul),
-                     pack_bf16x2(__uint_as_float(v[8 * q + 4]) * mul, __uint_as_float(v[8 * q + 5]) * mul),
-                     pack_bf16x2(__uint_as_float(v[8 * q + 6]) * mul, __uint_as_float(v[8 * q + 7]) * mul));
+                     pack_h2<F16>(__uint_as_float(v[8 * q]) * mul, __uint_as_float(v[8 * q + 1]) * mul),
+                     pack_h2<F16>(__uint_as_float(v[8 * q + 2]) * mul, __uint_as_float(v[8 * q + 3]) * mul),
+                     pack_h2<F16>(__uint_as_float(v[8 * q + 4]) * mul, __uint_as_float(v[8 * q + 5]) * mul),
+                     pack_h2<F16>(__uint_as_float(v[8 * q + 6]) * mul, __uint_as_float(v[8 * q + 7]) * mul));
 }
 
-template <bool CAUSAL, bool F32>
+template <bool CAUSAL, bool F32, bool F16>
 __global__ void __launch_bounds__(BWD_THREADS, 1)
 attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_constant__ CUtensorMap tmDO, const __grid_constant__ CUtensorMap tmOut,
                    const AttnBwdArgs p) {
@@ -405,8 +417,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
     if (warp == CTRL_WARP) {
         if (lane == 0) {
             LPI_TRACE(p, 1);
-            const uint32_t idesc_dq = idesc_bf16(TC_BM, 64, 0, 1);        // A K-major, B MN-major
-            const uint32_t idesc_kv = idesc_bf16(64, 64, 1, 1);           // M = 64: both MN-major
+            const uint32_t idesc_dq = idesc_h<F16>(TC_BM, 64, 0, 1);        // A K-major, B MN-major
+            const uint32_t idesc_kv = idesc_h<F16>(64, 64, 1, 1);           // M = 64: both MN-major
             const uint32_t q_lo = desc_lo_k(sQ), do_lo = desc_lo_k(sdO), k_lo = desc_lo_k(sK), v_lo = desc_lo_k(sV);
             const uint32_t qmn_lo = desc_lo_mn(sQ, 8192), domn_lo = desc_lo_mn(sdO, 8192), kmn_lo = desc_lo_mn(sK, 8192);
             const uint32_t ds_lo = desc_lo_k(sdS), dsmn_lo = desc_lo_mn(sdS, 8192), pmn_lo = desc_lo_mn(sP, 8192);
@@ -414,7 +426,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
             auto issue_sdp = [&](int n) {
                 const int jb = n / n_t, i = n - jb * n_t, u = n & 1;
                 const int kp = min(64, (L - 64 * jb + 15) & ~15);
-                const uint32_t idesc_s = idesc_bf16(TC_BM, kp, 0, 0);
+                const uint32_t idesc_s = idesc_h<F16>(TC_BM, kp, 0, 0);
                 const uint32_t qa = q_lo + i * TILE16, ka = k_lo + jb * HALF16, da = do_lo + i * TILE16, va = v_lo + jb * HALF16;
                 const uint32_t ts = tmem + 128 * u;
                 if (n == 0) { mbar_wait(bar_ld0, 0); LPI_TRACE(p, 2); tc_fence_after(); }
@@ -511,8 +523,8 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
                     }
                     const float d0 = p0 * (__uint_as_float(dv[2 * e]) - del_i);
                     const float d1 = p1 * (__uint_as_float(dv[2 * e + 1]) - del_i);
-                    pk[e] = pack_bf16x2(p0, p1);
-                    dk[e] = pack_bf16x2(d0, d1);
+                    pk[e] = pack_h2<F16>(p0, p1);
+                    dk[e] = pack_h2<F16>(d0, d1);
                 }
                 const uint32_t off = uint32_t(u) * TC_TILE + uint32_t(r) * 128u;
 #pragma unroll
@@ -539,7 +551,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
             if (F32) {
                 if (row < L) store_row_f32<32>(p.dqkv_f32 + (size_t(b) * L + row) * ld + h * 64 + 32 * half, v, p.scale);
             } else {
-                stage_row32_bf16(sP + i * TC_TILE, r, 4 * half, v, p.scale);   // the P slots are dead: every product has retired
+                stage_row32_h<F16>(sP + i * TC_TILE, r, 4 * half, v, p.scale);   // the P slots are dead: every product has retired
             }
         }
         if (!F32) {
@@ -586,7 +598,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
                             store_row_f32<32>(p.dqkv_f32 + (size_t(b) * L + key) * ld + (is_v ? 2 : 1) * size_t(D) + h * 64 + 32 * (part & 1), v,
                                               is_v ? 1.0f : p.scale);
                     } else {
-                        stage_row32_bf16(sStage + (is_v ? TC_TILE / 2 : 0), krow, 4 * (part & 1), v, is_v ? 1.0f : p.scale);
+                        stage_row32_h<F16>(sStage + (is_v ? TC_TILE / 2 : 0), krow, 4 * (part & 1), v, is_v ? 1.0f : p.scale);
                     }
                 }
             }
@@ -615,7 +627,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
 
 // 3-D view [B, L, cols] of a row-major [B*L, cols] bf16 matrix, box = [1, box_rows, 64 columns], SWIZZLE_128B;
 // rows past L (and past B) are zero-filled, so a tile never sees the next sample's tokens.
-static int make_tmap_rows3d(CUtensorMap* m, const void* ptr, int B, int L, int cols, int box_rows) {
+static int make_tmap_rows3d(CUtensorMap* m, const void* ptr, int B, int L, int cols, int box_rows, bool f16 = false) {
     if (int rc = ensure_tma_encoder()) return rc;
     if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (cols % 8)) return set_error(LPI_ERR_ARG, "attention: operand must be 16-byte aligned");
     static PFN_encodeTiled enc = nullptr;
@@ -630,7 +642,7 @@ static int make_tmap_rows3d(CUtensorMap* m, const void* ptr, int B, int L, int c
     cuuint64_t strides[2] = {cuuint64_t(cols) * 2, cuuint64_t(L) * cols * 2};
     cuuint32_t box[3] = {64, cuuint32_t(box_rows), 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = enc(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(LPI_ERR_CUDA, "attention: cuTensorMapEncodeTiled failed: %d", int(r));
     return 0;
@@ -645,55 +657,69 @@ bool attn_tc_enabled(int L) {
     return v == 1 && L <= TC_MAXL;
 }
 
-int attn_fwd_tc(const void* qkv, void* out, float* out_f32, float* lse2, int B, int L, int H, int causal, cudaStream_t st) {
+int attn_fwd_tc(const void* qkv, void* out, float* out_f32, float* lse2, int B, int L, int H, int causal, bool f16, cudaStream_t st) {
     const int D = H * 64;
     const int kv_rows = (L + 15) & ~15;
     CUtensorMap tmQ, tmKV;
-    if (int rc = make_tmap_rows3d(&tmQ, qkv, B, L, 3 * D, TC_BM)) return rc;
-    if (int rc = make_tmap_rows3d(&tmKV, qkv, B, L, 3 * D, kv_rows)) return rc;
+    if (int rc = make_tmap_rows3d(&tmQ, qkv, B, L, 3 * D, TC_BM, f16)) return rc;
+    if (int rc = make_tmap_rows3d(&tmKV, qkv, B, L, 3 * D, kv_rows, f16)) return rc;
     AttnFwdArgs a{static_cast<__nv_bfloat16*>(out), out_f32, lse2, L, H, kv_rows, 0.125f * 1.4426950408889634f, g_attn_trace};
     const dim3 grid((L + TC_BM - 1) / TC_BM, H, B);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e1 = cudaFuncSetAttribute(attn_fwd_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM);
-        cudaError_t e2 = cudaFuncSetAttribute(attn_fwd_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM);
-        if (e1 != cudaSuccess || e2 != cudaSuccess) return set_error(LPI_ERR_CUDA, "attn_fwd_tc: cudaFuncSetAttribute failed");
+        cudaError_t e = cudaSuccess;
+        auto set = [&](const void* k) { if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM); };
+        set(reinterpret_cast<const void*>(attn_fwd_tc_kernel<true, false>));
+        set(reinterpret_cast<const void*>(attn_fwd_tc_kernel<false, false>));
+        set(reinterpret_cast<const void*>(attn_fwd_tc_kernel<true, true>));
+        set(reinterpret_cast<const void*>(attn_fwd_tc_kernel<false, true>));
+        if (e != cudaSuccess) return set_error(LPI_ERR_CUDA, "attn_fwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         configured = true;
     }
-    if (causal) attn_fwd_tc_kernel<true><<<grid, FWD_THREADS, FWD_SMEM, st>>>(tmQ, tmKV, a);
-    else attn_fwd_tc_kernel<false><<<grid, FWD_THREADS, FWD_SMEM, st>>>(tmQ, tmKV, a);
+    if (causal) {
+        if (f16) attn_fwd_tc_kernel<true, true><<<grid, FWD_THREADS, FWD_SMEM, st>>>(tmQ, tmKV, a);
+        else attn_fwd_tc_kernel<true, false><<<grid, FWD_THREADS, FWD_SMEM, st>>>(tmQ, tmKV, a);
+    } else {
+        if (f16) attn_fwd_tc_kernel<false, true><<<grid, FWD_THREADS, FWD_SMEM, st>>>(tmQ, tmKV, a);
+        else attn_fwd_tc_kernel<false, false><<<grid, FWD_THREADS, FWD_SMEM, st>>>(tmQ, tmKV, a);
+    }
     return check_launch("attn_fwd_tc");
 }
 
 int attn_bwd_tc(const void* qkv, const void* d_out, const float* lse2, const float* delta, void* dqkv, float* dqkv_f32, int B, int L, int H,
-                int causal, cudaStream_t st) {
+                int causal, bool f16, cudaStream_t st) {
     const int D = H * 64;
     const int rows = (L + 15) & ~15;
+    if (f16 && dqkv_f32) return set_error(LPI_ERR_ARG, "attn_bwd: the fp16 path writes fp16 gradients only");
     CUtensorMap tmQKV, tmDO, tmOut;
-    if (int rc = make_tmap_rows3d(&tmQKV, qkv, B, L, 3 * D, rows)) return rc;
-    if (int rc = make_tmap_rows3d(&tmDO, d_out, B, L, D, rows)) return rc;
+    if (int rc = make_tmap_rows3d(&tmQKV, qkv, B, L, 3 * D, rows, f16)) return rc;
+    if (int rc = make_tmap_rows3d(&tmDO, d_out, B, L, D, rows, f16)) return rc;
     if (dqkv_f32) tmOut = tmQKV;                            // unused by the fp32 variant (direct stores)
-    else if (int rc = make_tmap_rows3d(&tmOut, dqkv, B, L, 3 * D, 64)) return rc;
+    else if (int rc = make_tmap_rows3d(&tmOut, dqkv, B, L, 3 * D, 64, f16)) return rc;
     AttnBwdArgs a{lse2, delta, static_cast<__nv_bfloat16*>(dqkv), dqkv_f32, L, H, rows, 0.125f, 0.125f * 1.4426950408889634f, g_attn_trace};
     const dim3 grid(H, B);
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaSuccess;
         auto set = [&](const void* k) { if (e == cudaSuccess) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM); };
-        set(reinterpret_cast<const void*>(attn_bwd_tc_kernel<true, true>));
-        set(reinterpret_cast<const void*>(attn_bwd_tc_kernel<true, false>));
-        set(reinterpret_cast<const void*>(attn_bwd_tc_kernel<false, true>));
-        set(reinterpret_cast<const void*>(attn_bwd_tc_kernel<false, false>));
+        set(reinterpret_cast<const void*>(attn_bwd_tc_kernel<true, true, false>));
+        set(reinterpret_cast<const void*>(attn_bwd_tc_kernel<true, false, false>));
+        set(reinterpret_cast<const void*>(attn_bwd_tc_kernel<false, true, false>));
+        set(reinterpret_cast<const void*>(attn_bwd_tc_kernel<false, false, false>));
+        set(reinterpret_cast<const void*>(attn_bwd_tc_kernel<true, false, true>));
+        set(reinterpret_cast<const void*>(attn_bwd_tc_kernel<false, false, true>));
         if (e != cudaSuccess) return set_error(LPI_ERR_CUDA, "attn_bwd_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         configured = true;
     }
     const bool f32 = dqkv_f32 != nullptr;
     if (causal) {
-        if (f32) attn_bwd_tc_kernel<true, true><<<grid, BWD_THREADS, BWD_SMEM, st>>>(tmQKV, tmDO, tmOut, a);
-        else attn_bwd_tc_kernel<true, false><<<grid, BWD_THREADS, BWD_SMEM, st>>>(tmQKV, tmDO, tmOut, a);
+        if (f16) attn_bwd_tc_kernel<true, false, true><<<grid, BWD_THREADS, BWD_SMEM, st>>>(tmQKV, tmDO, tmOut, a);
+        else if (f32) attn_bwd_tc_kernel<true, true, false><<<grid, BWD_THREADS, BWD_SMEM, st>>>(tmQKV, tmDO, tmOut, a);
+        else attn_bwd_tc_kernel<true, false, false><<<grid, BWD_THREADS, BWD_SMEM, st>>>(tmQKV, tmDO, tmOut, a);
     } else {
-        if (f32) attn_bwd_tc_kernel<false, true><<<grid, BWD_THREADS, BWD_SMEM, st>>>(tmQKV, tmDO, tmOut, a);
-        else attn_bwd_tc_kernel<false, false><<<grid, BWD_THREADS, BWD_SMEM, st>>>(tmQKV, tmDO, tmOut, a);
+        if (f16) attn_bwd_tc_kernel<false, false, true><<<grid, BWD_THREADS, BWD_SMEM, st>>>(tmQKV, tmDO, tmOut, a);
+        else if (f32) attn_bwd_tc_kernel<false, true, false><<<grid, BWD_THREADS, BWD_SMEM, st>>>(tmQKV, tmDO, tmOut, a);
+        else attn_bwd_tc_kernel<false, false, false><<<grid, BWD_THREADS, BWD_SMEM, st>>>(tmQKV, tmDO, tmOut, a);
     }
     return check_launch("attn_bwd_tc");
 }

@@ -4,6 +4,7 @@
 // Reference: retrieval/models/clip/model.py:154-160 (LayerNorm in fp32), :227-259 (VisionTransformer.forward),
 // retrieval/models/clip/prompt_learner.py:52-63,128-163 (TextEncoder / PromptLearner), retrieval/models/slinet.py:122,133.
 // All rows are [tokens, D] fp32 (residual stream) or bf16 (GEMM operands); one warp per row, 16-byte accesses.
+#include <cuda_fp16.h>
 #include "ptx.cuh"
 #include "lpi_internal.h"
 
@@ -29,7 +30,17 @@ __device__ __forceinline__ RowStats row_stats(const float4 (&v)[NV], int D, floa
     return {mean, rsqrtf(var + eps)};
 }
 
-template <int NV>
+// 16-bit shadows are bf16 (vision tower) or fp16 (F16: text tower, see gemm.cu)
+template <bool F16>
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+    if (F16) {
+        const __half2 v = __floats2half2_rn(lo, hi);
+        return *reinterpret_cast<const uint32_t*>(&v);
+    }
+    return pack_bf16x2(lo, hi);
+}
+
+template <int NV, bool F16 = false>
 __device__ __forceinline__ void ln_apply_store(const float4 (&v)[NV], RowStats st, const float* gamma, const float* beta, int lane,
                                                float* out_f32, __nv_bfloat16* out_bf16) {
 #pragma unroll
@@ -42,12 +53,12 @@ __device__ __forceinline__ void ln_apply_store(const float4 (&v)[NV], RowStats s
         y.z = (v[i].z - st.mean) * st.rstd * g.z + b.z;
         y.w = (v[i].w - st.mean) * st.rstd * g.w + b.w;
         if (out_f32) *reinterpret_cast<float4*>(out_f32 + c) = y;
-        if (out_bf16) *reinterpret_cast<uint2*>(out_bf16 + c) = make_uint2(pack_bf16x2(y.x, y.y), pack_bf16x2(y.z, y.w));
+        if (out_bf16) *reinterpret_cast<uint2*>(out_bf16 + c) = make_uint2(pack_h2<F16>(y.x, y.y), pack_h2<F16>(y.z, y.w));
     }
 }
 
 // ------------------------------------------------------------------------------------------------ LayerNorm
-template <int NV>
+template <int NV, bool F16 = false>
 __global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                                      float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16, long M, int D, float eps) {
     const long row = (long(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -57,7 +68,7 @@ __global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* _
 #pragma unroll
     for (int i = 0; i < NV; ++i) v[i] = *reinterpret_cast<const float4*>(x + row * D + (i * 32 + lane) * 4);
     const RowStats st = row_stats<NV>(v, D, eps);
-    ln_apply_store<NV>(v, st, gamma, beta, lane, out_f32 ? out_f32 + row * D : nullptr, out_bf16 ? out_bf16 + row * D : nullptr);
+    ln_apply_store<NV, F16>(v, st, gamma, beta, lane, out_f32 ? out_f32 + row * D : nullptr, out_bf16 ? out_bf16 + row * D : nullptr);
 }
 
 // dx = rstd * (gdy - mean(gdy) - xhat * mean(gdy * xhat)),  gdy = gamma * dy;   g = (accumulate ? g : 0) + dx
@@ -89,9 +100,12 @@ __device__ __forceinline__ void ln_bwd_row(const float4 (&xv)[NV], const float4 
     }
 }
 
-template <int NV>
+// F16: the fp16 gradient path carries gradients multiplied by `shadow_scale` (a power of two) so small values stay in fp16's
+// normal range: dy arrives scaled (dy_scale = 1 / shadow_scale brings it back), g stays true-scale fp32, the shadow is scaled again.
+template <int NV, bool F16 = false>
 __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
-                                     float* __restrict__ g, __nv_bfloat16* __restrict__ g_bf16, long M, int D, float eps, int accumulate) {
+                                     float* __restrict__ g, __nv_bfloat16* __restrict__ g_bf16, long M, int D, float eps, int accumulate,
+                                     float dy_scale = 1.0f, float shadow_scale = 1.0f) {
     const long row = (long(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     if (row >= M) return;
     const int lane = threadIdx.x & 31;
@@ -101,6 +115,7 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const float* 
         const long o = row * D + (i * 32 + lane) * 4;
         xv[i] = *reinterpret_cast<const float4*>(x + o);
         dyv[i] = *reinterpret_cast<const float4*>(dy + o);
+        if (F16) { dyv[i].x *= dy_scale; dyv[i].y *= dy_scale; dyv[i].z *= dy_scale; dyv[i].w *= dy_scale; }
     }
     ln_bwd_row<NV>(xv, dyv, gamma, D, eps, lane, dx);
 #pragma unroll
@@ -112,7 +127,10 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const float* 
             r.x += p.x; r.y += p.y; r.z += p.z; r.w += p.w;
         }
         *reinterpret_cast<float4*>(g + o) = r;
-        if (g_bf16) *reinterpret_cast<uint2*>(g_bf16 + o) = make_uint2(pack_bf16x2(r.x, r.y), pack_bf16x2(r.z, r.w));
+        if (g_bf16) {
+            if (F16) { r.x *= shadow_scale; r.y *= shadow_scale; r.z *= shadow_scale; r.w *= shadow_scale; }
+            *reinterpret_cast<uint2*>(g_bf16 + o) = make_uint2(pack_h2<F16>(r.x, r.y), pack_h2<F16>(r.z, r.w));
+        }
     }
 }
 
@@ -244,17 +262,19 @@ __global__ void inject_prompt_rows_kernel(float* __restrict__ x, const float* __
 
 // ------------------------------------------------------------------------------------------------ encoder heads
 // feat[b] = normalize( LN(x[row_idx[b]]) @ proj ),  proj [D, E] row-major (model.py:254-257, prompt_learner.py:57-61, slinet.py:122,133)
-// grid = (ceil(B/HB), E/128): a block normalises HB rows into smem (cheap, recomputed per column slice) and produces a
-// 128-wide slice of the projection for them; the L2 normalisation over E follows in head_norm_kernel.
-constexpr int HB = 4;
-__global__ void __launch_bounds__(128)
+// grid = (ceil(B/HB), E/32): a block normalises HB rows into smem (cheap, recomputed per column slice) and produces a 32-wide
+// slice of the projection for them with the D-long reduction split over its 8 warps (partials combined through smem); the L2
+// normalisation over E follows in head_norm_kernel.
+constexpr int HB = 8;
+__global__ void __launch_bounds__(256)
 head_fwd_kernel(const float* __restrict__ x, const int* __restrict__ row_idx, const float* __restrict__ gamma, const float* __restrict__ beta,
                 const float* __restrict__ proj, float* __restrict__ z_out, int B, int D, int E, float eps) {
-    extern __shared__ float sm[];                    // y[HB][D]
+    extern __shared__ float sm[];                    // y[HB][D] | part[8][HB][32]
     float* y = sm;
+    float* part = sm + HB * D;
     const int b0 = blockIdx.x * HB;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (b0 + warp < B) {                             // 4 warps: one row each
+    if (b0 + warp < B) {                             // 8 warps: one row each
         const float* xr = x + long(row_idx[b0 + warp]) * D;
         float s = 0.f;
         for (int c = lane; c < D; c += 32) s += xr[c];
@@ -267,23 +287,31 @@ head_fwd_kernel(const float* __restrict__ x, const int* __restrict__ row_idx, co
         for (int c = lane; c < D; c += 32) y[warp * D + c] = 0.f;
     }
     __syncthreads();
-    const int e = blockIdx.y * 128 + threadIdx.x;
-    if (e >= E) return;
+    const int e = blockIdx.y * 32 + lane;
     float acc[HB];
 #pragma unroll
     for (int h = 0; h < HB; ++h) acc[h] = 0.f;
-    for (int k0 = 0; k0 < D; k0 += 16) {             // 16 independent weight loads in flight per thread (D % 16 == 0)
-        float w[16];
+    if (e < E) {
+        const int kspan = D / 8;                     // D % 64 == 0 for every supported width
+        for (int k0 = warp * kspan; k0 < (warp + 1) * kspan; k0 += 8) {
+            float w[8];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) w[i] = __ldg(proj + long(k0 + i) * E + e);
+            for (int i = 0; i < 8; ++i) w[i] = __ldg(proj + long(k0 + i) * E + e);
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
+            for (int i = 0; i < 8; ++i)
 #pragma unroll
-            for (int h = 0; h < HB; ++h) acc[h] = fmaf(y[h * D + k0 + i], w[i], acc[h]);
+                for (int h = 0; h < HB; ++h) acc[h] = fmaf(y[h * D + k0 + i], w[i], acc[h]);
+        }
     }
 #pragma unroll
-    for (int h = 0; h < HB; ++h)
-        if (b0 + h < B) z_out[long(b0 + h) * E + e] = acc[h];
+    for (int h = 0; h < HB; ++h) part[(warp * HB + h) * 32 + lane] = acc[h];
+    __syncthreads();
+    {                                                // warp w finishes sample w
+        float v = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) v += part[(w * HB + warp) * 32 + lane];
+        if (e < E && b0 + warp < B) z_out[long(b0 + warp) * E + e] = v;
+    }
 }
 
 // feat[b] = z[b] / ||z[b]||   (one warp per sample)
@@ -296,88 +324,77 @@ __global__ void head_norm_kernel(const float* __restrict__ z, float* __restrict_
     for (int e = lane; e < E; e += 32) feat[long(b) * E + e] = z[long(b) * E + e] * inv;
 }
 
-// Backward of the head for one sample per block: (dfeat -> dz via the L2-norm backward) + dz_direct -> dy = dz @ proj^T
-// -> LN bwd -> g[row] (assigned).  dfeat = gradient wrt the normalised feature, dz_direct = gradient wrt the raw projection
-// (what VisionTransformer.forward / TextEncoder.forward return in the reference); either may be NULL.
+// Backward of the head in two kernels (the first version ran everything for one sample in one block: 64 blocks, each streaming
+// the whole 1.5 MB projection through a serial loop -- 251 us for 25 MFLOP):
+//   head_bwd_dy_kernel : (dfeat -> dz via the L2-norm backward) + dz_direct, then dy = dz @ proj^T for HBB samples x 64 rows of proj
+//                        per block; dy is parked in g[row_idx[b], :] (those rows are assigned by this op anyway)
+//   head_bwd_ln_kernel : one warp per sample: LN backward of the parked dy in place, plus the bf16 shadow
+// dfeat = gradient wrt the normalised feature, dz_direct = gradient wrt the raw projection (what VisionTransformer.forward /
+// TextEncoder.forward return in the reference); either may be NULL.
+constexpr int HBB = 8;
 __global__ void __launch_bounds__(256)
-head_bwd_kernel(const float* __restrict__ dfeat, const float* __restrict__ dz_direct, const float* __restrict__ z, const float* __restrict__ x,
-                const int* __restrict__ row_idx, const float* __restrict__ gamma, const float* __restrict__ proj, float* __restrict__ g,
-                __nv_bfloat16* __restrict__ g_bf16, int D, int E, float eps) {
-    extern __shared__ float sm[];                    // dz[E] | dy[D] | red[16]
-    float* dz = sm;
-    float* dy = sm + E;
-    float* red = dy + D;
-    const int b = blockIdx.x;
+head_bwd_dy_kernel(const float* __restrict__ dfeat, const float* __restrict__ dz_direct, const float* __restrict__ z,
+                   const int* __restrict__ row_idx, const float* __restrict__ proj, float* __restrict__ g, int B, int D, int E) {
+    extern __shared__ float sm[];                    // dz[HBB][E]
+    const int b0 = blockIdx.x * HBB;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const float* zr = z + long(b) * E;
-    const float* dfr = dfeat ? dfeat + long(b) * E : nullptr;
-    float a = 0.f, c = 0.f;
-    for (int e = threadIdx.x; e < E; e += 256) { a += zr[e] * zr[e]; c += dfr ? zr[e] * dfr[e] : 0.f; }
-    a = warp_sum(a); c = warp_sum(c);
-    if (lane == 0) { red[warp] = a; red[8 + warp] = c; }
-    __syncthreads();
-    float nn = 0.f, zd = 0.f;
-    for (int w = 0; w < 8; ++w) { nn += red[w]; zd += red[8 + w]; }
-    const float inv = 1.f / sqrtf(nn);
-    // f = z*inv ; dz = (df - f (f.df)) * inv ,  f.df = zd * inv
-    for (int e = threadIdx.x; e < E; e += 256) {
-        float v = dfr ? (dfr[e] - zr[e] * inv * (zd * inv)) * inv : 0.f;
-        if (dz_direct) v += dz_direct[long(b) * E + e];
-        dz[e] = v;
-    }
-    __syncthreads();
-    for (int k = warp * 4; k < D; k += 32) {         // dy[k] = sum_e dz[e] proj[k, e]: a warp takes 4 rows of proj at a time
-        float s4[4] = {0.f, 0.f, 0.f, 0.f};
+    if (b0 + warp < B) {                             // 8 warps: one sample each.  f = z*inv ; dz = (df - f (f.df)) * inv
+        const int b = b0 + warp;
+        const float* zr = z + long(b) * E;
+        const float* dfr = dfeat ? dfeat + long(b) * E : nullptr;
+        float a = 0.f, c = 0.f;
+        for (int e = lane; e < E; e += 32) { a += zr[e] * zr[e]; c += dfr ? zr[e] * dfr[e] : 0.f; }
+        a = warp_sum(a); c = warp_sum(c);
+        const float inv = 1.f / sqrtf(a);
         for (int e = lane; e < E; e += 32) {
-            const float d = dz[e];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) s4[i] = fmaf(d, __ldg(proj + long(k + i) * E + e), s4[i]);
+            float v = dfr ? (dfr[e] - zr[e] * inv * (c * inv)) * inv : 0.f;
+            if (dz_direct) v += dz_direct[long(b) * E + e];
+            sm[warp * E + e] = v;
         }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float v = warp_sum(s4[i]);
-            if (lane == 0) dy[k + i] = v;
-        }
+    } else {
+        for (int e = lane; e < E; e += 32) sm[warp * E + e] = 0.f;
     }
     __syncthreads();
-    // LN backward over the row (block-wide)
+    const int k_end = min(D, (blockIdx.y + 1) * 64);
+    for (int k = blockIdx.y * 64 + warp; k < k_end; k += 8) {          // dy[b, k] = sum_e dz[b, e] proj[k, e]
+        float acc[HBB];
+#pragma unroll
+        for (int h = 0; h < HBB; ++h) acc[h] = 0.f;
+        for (int e = lane; e < E; e += 32) {
+            const float w = __ldg(proj + long(k) * E + e);
+#pragma unroll
+            for (int h = 0; h < HBB; ++h) acc[h] = fmaf(sm[h * E + e], w, acc[h]);
+        }
+#pragma unroll
+        for (int h = 0; h < HBB; ++h) {
+            const float v = warp_sum(acc[h]);
+            if (lane == 0 && b0 + h < B) g[long(row_idx[b0 + h]) * D + k] = v;
+        }
+    }
+}
+
+template <int NV, bool F16 = false>
+__global__ void head_bwd_ln_kernel(const float* __restrict__ x, const int* __restrict__ row_idx, const float* __restrict__ gamma,
+                                   float* __restrict__ g, __nv_bfloat16* __restrict__ g_bf16, int B, int D, float eps, float shadow_scale = 1.0f) {
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (b >= B) return;
     const long row = row_idx[b];
-    const float* xr = x + row * D;
-    float s = 0.f;
-    for (int k = threadIdx.x; k < D; k += 256) s += xr[k];
-    s = warp_sum(s);
-    __syncthreads();
-    if (lane == 0) red[warp] = s;
-    __syncthreads();
-    float mean = 0.f;
-    for (int w = 0; w < 8; ++w) mean += red[w];
-    mean /= D;
-    float q = 0.f;
-    for (int k = threadIdx.x; k < D; k += 256) { const float d = xr[k] - mean; q += d * d; }
-    q = warp_sum(q);
-    __syncthreads();
-    if (lane == 0) red[warp] = q;
-    __syncthreads();
-    float var = 0.f;
-    for (int w = 0; w < 8; ++w) var += red[w];
-    const float rstd = rsqrtf(var / D + eps);
-    float s1 = 0.f, s2 = 0.f;
-    for (int k = threadIdx.x; k < D; k += 256) {
-        const float gd = gamma[k] * dy[k];
-        s1 += gd;
-        s2 += gd * (xr[k] - mean) * rstd;
+    float4 xv[NV], dyv[NV], dx[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const long o = row * D + (i * 32 + lane) * 4;
+        xv[i] = *reinterpret_cast<const float4*>(x + o);
+        dyv[i] = *reinterpret_cast<const float4*>(g + o);
     }
-    s1 = warp_sum(s1); s2 = warp_sum(s2);
-    __syncthreads();
-    if (lane == 0) { red[warp] = s1; red[8 + warp] = s2; }
-    __syncthreads();
-    float m1 = 0.f, m2 = 0.f;
-    for (int w = 0; w < 8; ++w) { m1 += red[w]; m2 += red[8 + w]; }
-    m1 /= D; m2 /= D;
-    for (int k = threadIdx.x; k < D; k += 256) {
-        const float v = rstd * (gamma[k] * dy[k] - m1 - (xr[k] - mean) * rstd * m2);
-        g[row * D + k] = v;
-        if (g_bf16) g_bf16[row * D + k] = __float2bfloat16_rn(v);
+    ln_bwd_row<NV>(xv, dyv, gamma, D, eps, lane, dx);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const long o = row * D + (i * 32 + lane) * 4;
+        *reinterpret_cast<float4*>(g + o) = dx[i];
+        if (g_bf16) {
+            const float m = F16 ? shadow_scale : 1.0f;
+            *reinterpret_cast<uint2*>(g_bf16 + o) = make_uint2(pack_h2<F16>(dx[i].x * m, dx[i].y * m), pack_h2<F16>(dx[i].z * m, dx[i].w * m));
+        }
     }
 }
 
@@ -410,6 +427,32 @@ extern "C" int lpi_layernorm_fwd(const float* x, const float* gamma, const float
         return 0;
     });
     return rc ? rc : check_launch("layernorm_fwd");
+}
+
+extern "C" int lpi_layernorm_fwd_f16(const float* x, const float* gamma, const float* beta, float* out_f32, void* out_f16, long long M, int D,
+                                     float eps, void* stream) {
+    if (M <= 0) return LPI_OK;
+    if (!out_f32 && !out_f16) return set_error(LPI_ERR_ARG, "layernorm_fwd_f16: no output");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int rc = dispatch_nv(D, [&](auto nv) {
+        layernorm_fwd_kernel<decltype(nv)::value, true><<<warp_grid(M, 256), 256, 0, st>>>(x, gamma, beta, out_f32,
+                                                                                          static_cast<__nv_bfloat16*>(out_f16), M, D, eps);
+        return 0;
+    });
+    return rc ? rc : check_launch("layernorm_fwd_f16");
+}
+
+extern "C" int lpi_layernorm_bwd_f16(const float* dy_scaled, const float* x, const float* gamma, float* g, void* g_f16, long long M, int D,
+                                     float eps, int accumulate, float grad_scale, void* stream) {
+    if (M <= 0) return LPI_OK;
+    if (!(grad_scale > 0.f)) return set_error(LPI_ERR_ARG, "layernorm_bwd_f16: grad_scale must be positive");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int rc = dispatch_nv(D, [&](auto nv) {
+        layernorm_bwd_kernel<decltype(nv)::value, true><<<warp_grid(M, 128), 128, 0, st>>>(dy_scaled, x, gamma, g, static_cast<__nv_bfloat16*>(g_f16),
+                                                                                          M, D, eps, accumulate, 1.0f / grad_scale, grad_scale);
+        return 0;
+    });
+    return rc ? rc : check_launch("layernorm_bwd_f16");
 }
 
 extern "C" int lpi_layernorm_bwd(const float* dy, const float* x, const float* gamma, float* g, void* g_bf16, long long M, int D, float eps,
@@ -488,19 +531,40 @@ extern "C" int lpi_inject_prompt_rows(float* x, const float* prompt, const int* 
 extern "C" int lpi_head_fwd(const float* x, const int* row_idx, const float* ln_gamma, const float* ln_beta, const float* proj, float* z_out,
                             float* feat_out, int B, int D, int E, float eps, void* stream) {
     if (B <= 0) return LPI_OK;
-    const int smem = HB * D * sizeof(float);
+    if (D % 64) return set_error(LPI_ERR_ARG, "head_fwd: D=%d must be a multiple of 64", D);
+    const int smem = (HB * D + 8 * HB * 32) * sizeof(float);
+    if (smem > 48 * 1024) return set_error(LPI_ERR_UNSUPPORTED, "head_fwd: D=%d too wide", D);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    head_fwd_kernel<<<dim3((B + HB - 1) / HB, (E + 127) / 128), 128, smem, st>>>(x, row_idx, ln_gamma, ln_beta, proj, z_out, B, D, E, eps);
+    head_fwd_kernel<<<dim3((B + HB - 1) / HB, (E + 31) / 32), 256, smem, st>>>(x, row_idx, ln_gamma, ln_beta, proj, z_out, B, D, E, eps);
     head_norm_kernel<<<(B * 32 + 255) / 256, 256, 0, st>>>(z_out, feat_out, B, E);
     return check_launch("head_fwd");
 }
 
-extern "C" int lpi_head_bwd(const float* dfeat, const float* dz_direct, const float* z, const float* x, const int* row_idx,
-                            const float* ln_gamma, const float* proj, float* g, void* g_bf16, int B, int D, int E, float eps, void* stream) {
+static int head_bwd_impl(const float* dfeat, const float* dz_direct, const float* z, const float* x, const int* row_idx, const float* ln_gamma,
+                         const float* proj, float* g, void* g_bf16, int B, int D, int E, float eps, bool f16, float shadow_scale, void* stream) {
     if (B <= 0) return LPI_OK;
     if (!dfeat && !dz_direct) return set_error(LPI_ERR_ARG, "head_bwd: no upstream gradient");
-    const int smem = (E + D + 16) * sizeof(float);
-    head_bwd_kernel<<<B, 256, smem, static_cast<cudaStream_t>(stream)>>>(dfeat, dz_direct, z, x, row_idx, ln_gamma, proj, g,
-                                                                         static_cast<__nv_bfloat16*>(g_bf16), D, E, eps);
-    return check_launch("head_bwd");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int smem = HBB * E * sizeof(float);
+    if (smem > 48 * 1024) return set_error(LPI_ERR_UNSUPPORTED, "head_bwd: E=%d too wide", E);
+    head_bwd_dy_kernel<<<dim3((B + HBB - 1) / HBB, (D + 63) / 64), 256, smem, st>>>(dfeat, dz_direct, z, row_idx, proj, g, B, D, E);
+    const int rc = dispatch_nv(D, [&](auto nv) {
+        constexpr int NV = decltype(nv)::value;
+        auto gb = static_cast<__nv_bfloat16*>(g_bf16);
+        if (f16) head_bwd_ln_kernel<NV, true><<<(B * 32 + 127) / 128, 128, 0, st>>>(x, row_idx, ln_gamma, g, gb, B, D, eps, shadow_scale);
+        else head_bwd_ln_kernel<NV, false><<<(B * 32 + 127) / 128, 128, 0, st>>>(x, row_idx, ln_gamma, g, gb, B, D, eps, 1.0f);
+        return 0;
+    });
+    return rc ? rc : check_launch("head_bwd");
+}
+
+extern "C" int lpi_head_bwd(const float* dfeat, const float* dz_direct, const float* z, const float* x, const int* row_idx,
+                            const float* ln_gamma, const float* proj, float* g, void* g_bf16, int B, int D, int E, float eps, void* stream) {
+    return head_bwd_impl(dfeat, dz_direct, z, x, row_idx, ln_gamma, proj, g, g_bf16, B, D, E, eps, false, 1.0f, stream);
+}
+
+extern "C" int lpi_head_bwd_f16(const float* dfeat, const float* dz_direct, const float* z, const float* x, const int* row_idx,
+                                const float* ln_gamma, const float* proj, float* g, void* g_f16, float grad_scale, int B, int D, int E, float eps,
+                                void* stream) {
+    return head_bwd_impl(dfeat, dz_direct, z, x, row_idx, ln_gamma, proj, g, g_f16, B, D, E, eps, true, grad_scale, stream);
 }

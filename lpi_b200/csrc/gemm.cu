@@ -17,6 +17,7 @@
 //                   of its query row ordered by (score desc, gallery index asc).
 #include "ptx.cuh"
 #include "lpi_internal.h"
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 namespace lpi {
@@ -151,7 +152,23 @@ __device__ __forceinline__ float quick_gelu_grad(float z) {
 // covering one row: every instruction moves 4 rows x 128 B (fp32) or 4 x 64 B (bf16) in full sectors.
 __device__ __forceinline__ float4 f4_add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 
-template <int EPI>
+// 16-bit outputs / saved pre-activations are bf16 (vision tower) or fp16 (F16 = true: the text tower, whose operands need the
+// 10-bit mantissa -- same precision class as TF32 at the full kind::f16 rate and half the operand bytes)
+template <bool F16>
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+    if (F16) {
+        const __half2 v = __floats2half2_rn(lo, hi);
+        return *reinterpret_cast<const uint32_t*>(&v);
+    }
+    return pack_bf16x2(lo, hi);
+}
+template <bool F16>
+__device__ __forceinline__ float2 unpack_h2(uint32_t w) {
+    if (F16) return __half22float2(*reinterpret_cast<const __half2*>(&w));
+    return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
+}
+
+template <int EPI, bool F16 = false>
 __device__ __forceinline__ void epilogue_block(const GemmArgs& p, const float4* __restrict__ st, int row0, int col0, int lane) {
     constexpr bool kBias = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_F32 ||
                             EPI == EPI_BIAS_GELU_F32);
@@ -197,7 +214,7 @@ __device__ __forceinline__ void epilogue_block(const GemmArgs& p, const float4* 
             }
             *reinterpret_cast<float4*>(p.out_f32 + off) = v[i];
             if ((EPI == EPI_BIAS_RESID_F32 || EPI == EPI_ACC_F32) && p.out_bf16)
-                *reinterpret_cast<uint2*>(p.out_bf16 + off) = make_uint2(pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));
+                *reinterpret_cast<uint2*>(p.out_bf16 + off) = make_uint2(pack_h2<F16>(v[i].x, v[i].y), pack_h2<F16>(v[i].z, v[i].w));
         }
     } else {
         if (EPI == EPI_DGELU_BF16) {
@@ -207,10 +224,10 @@ __device__ __forceinline__ void epilogue_block(const GemmArgs& p, const float4* 
                 e[i] = (i * 4 + rsub < rows) ? *reinterpret_cast<const uint2*>(p.aux_bf16 + base + size_t(i * 4) * p.ldo) : make_uint2(0u, 0u);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const float2 z0 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&e[i].x));
-                const float2 z1 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&e[i].y));
-                v[i].x *= quick_gelu_grad(z0.x); v[i].y *= quick_gelu_grad(z0.y);
-                v[i].z *= quick_gelu_grad(z1.x); v[i].w *= quick_gelu_grad(z1.y);
+                const float2 z0 = unpack_h2<F16>(e[i].x);
+                const float2 z1 = unpack_h2<F16>(e[i].y);
+                v[i].x *= quick_gelu_grad<F16>(z0.x); v[i].y *= quick_gelu_grad<F16>(z0.y);
+                v[i].z *= quick_gelu_grad<F16>(z1.x); v[i].w *= quick_gelu_grad<F16>(z1.y);
             }
         }
 #pragma unroll
@@ -218,10 +235,10 @@ __device__ __forceinline__ void epilogue_block(const GemmArgs& p, const float4* 
             if (i * 4 + rsub >= rows) continue;
             const size_t off = base + size_t(i * 4) * p.ldo;
             if (EPI == EPI_BIAS_GELU_BF16) {
-                if (p.out2_bf16) *reinterpret_cast<uint2*>(p.out2_bf16 + off) = make_uint2(pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));
-                v[i] = make_float4(quick_gelu(v[i].x), quick_gelu(v[i].y), quick_gelu(v[i].z), quick_gelu(v[i].w));
+                if (p.out2_bf16) *reinterpret_cast<uint2*>(p.out2_bf16 + off) = make_uint2(pack_h2<F16>(v[i].x, v[i].y), pack_h2<F16>(v[i].z, v[i].w));
+                v[i] = make_float4(quick_gelu<F16>(v[i].x), quick_gelu<F16>(v[i].y), quick_gelu<F16>(v[i].z), quick_gelu<F16>(v[i].w));
             }
-            *reinterpret_cast<uint2*>(p.out_bf16 + off) = make_uint2(pack_bf16x2(v[i].x, v[i].y), pack_bf16x2(v[i].z, v[i].w));
+            *reinterpret_cast<uint2*>(p.out_bf16 + off) = make_uint2(pack_h2<F16>(v[i].x, v[i].y), pack_h2<F16>(v[i].z, v[i].w));
         }
     }
 }
@@ -472,10 +489,14 @@ struct PairCfg {
     static constexpr int TMEM_COLS = 512;
 };
 
-template <int MODE, int EPI, bool TF32>
+enum { OP_BF16 = 0, OP_TF32 = 1, OP_F16 = 2 };      // operand type of the CTA-pair GEMM
+
+template <int MODE, int EPI, int OP>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs p) {
     using C = PairCfg<MODE>;
+    constexpr bool TF32 = OP == OP_TF32;
+    constexpr bool F16 = OP == OP_F16;
     constexpr int BN = C::BN;
     constexpr int BKE = TF32 ? 32 : BK;
     extern __shared__ uint8_t smem_raw[];
@@ -569,7 +590,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer (leader CTA, single thread)
         if (leader && lane == 0) {
-            constexpr uint32_t idesc = make_idesc(TF32 ? kFmtTF32 : kFmtBF16, 2 * BM, BN, 0, 0);
+            constexpr uint32_t idesc = make_idesc(TF32 ? kFmtTF32 : (F16 ? kFmtF16 : kFmtBF16), 2 * BM, BN, 0, 0);
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0, aphase = 0;
             for (int t = cluster_id; t < total; t += n_clusters) {
@@ -642,7 +663,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             stg[lane * 8 + (j ^ (lane & 7))] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
                                                                            __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
                         __syncwarp();
-                        epilogue_block<EPI>(p, stg, m0 + quad * 32, n0 + c * 32, lane);
+                        epilogue_block<EPI, F16>(p, stg, m0 + quad * 32, n0 + c * 32, lane);
                         __syncwarp();
                     }
                 } else {
@@ -737,9 +758,9 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs
     return 0;
 }
 
-template <int MODE, int EPI, bool TF32>
+template <int MODE, int EPI, int OP>
 static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, int n_clusters, cudaStream_t st) {
-    auto kern = gemm_pair_kernel<MODE, EPI, TF32>;
+    auto kern = gemm_pair_kernel<MODE, EPI, OP>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<MODE>::SMEM_BYTES);
@@ -763,19 +784,20 @@ static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     return 0;
 }
 
-template <bool TF32>
+template <int OP>
 static int launch_pair_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, int n_clusters, cudaStream_t st) {
+    constexpr bool TF32 = OP == OP_TF32;
     switch (a.epi) {
-        case EPI_BIAS_BF16: return launch_pair<MODE_GEMM, EPI_BIAS_BF16, TF32>(tmA, tmB, a, n_clusters, st);
-        case EPI_BIAS_RESID_F32: return launch_pair<MODE_GEMM, EPI_BIAS_RESID_F32, TF32>(tmA, tmB, a, n_clusters, st);
-        case EPI_F32: return launch_pair<MODE_GEMM, EPI_F32, TF32>(tmA, tmB, a, n_clusters, st);
-        case EPI_BF16: return launch_pair<MODE_GEMM, EPI_BF16, TF32>(tmA, tmB, a, n_clusters, st);
-        case EPI_BIAS_GELU_BF16: if (!TF32) return launch_pair<MODE_GEMM, EPI_BIAS_GELU_BF16, false>(tmA, tmB, a, n_clusters, st); break;
-        case EPI_DGELU_BF16: if (!TF32) return launch_pair<MODE_GEMM, EPI_DGELU_BF16, false>(tmA, tmB, a, n_clusters, st); break;
-        case EPI_BIAS_F32: if (!TF32) return launch_pair<MODE_GEMM, EPI_BIAS_F32, false>(tmA, tmB, a, n_clusters, st); break;
-        case EPI_ACC_F32: if (!TF32) return launch_pair<MODE_GEMM, EPI_ACC_F32, false>(tmA, tmB, a, n_clusters, st); break;
-        case EPI_BIAS_GELU_F32: if (TF32) return launch_pair<MODE_GEMM, EPI_BIAS_GELU_F32, true>(tmA, tmB, a, n_clusters, st); break;
-        case EPI_DGELU_F32: if (TF32) return launch_pair<MODE_GEMM, EPI_DGELU_F32, true>(tmA, tmB, a, n_clusters, st); break;
+        case EPI_BIAS_BF16: return launch_pair<MODE_GEMM, EPI_BIAS_BF16, OP>(tmA, tmB, a, n_clusters, st);
+        case EPI_BIAS_RESID_F32: return launch_pair<MODE_GEMM, EPI_BIAS_RESID_F32, OP>(tmA, tmB, a, n_clusters, st);
+        case EPI_F32: return launch_pair<MODE_GEMM, EPI_F32, OP>(tmA, tmB, a, n_clusters, st);
+        case EPI_BF16: return launch_pair<MODE_GEMM, EPI_BF16, OP>(tmA, tmB, a, n_clusters, st);
+        case EPI_BIAS_GELU_BF16: if (!TF32) return launch_pair<MODE_GEMM, EPI_BIAS_GELU_BF16, TF32 ? OP_BF16 : OP>(tmA, tmB, a, n_clusters, st); break;
+        case EPI_DGELU_BF16: if (!TF32) return launch_pair<MODE_GEMM, EPI_DGELU_BF16, TF32 ? OP_BF16 : OP>(tmA, tmB, a, n_clusters, st); break;
+        case EPI_BIAS_F32: if (!TF32) return launch_pair<MODE_GEMM, EPI_BIAS_F32, TF32 ? OP_BF16 : OP>(tmA, tmB, a, n_clusters, st); break;
+        case EPI_ACC_F32: if (!TF32) return launch_pair<MODE_GEMM, EPI_ACC_F32, TF32 ? OP_BF16 : OP>(tmA, tmB, a, n_clusters, st); break;
+        case EPI_BIAS_GELU_F32: if (TF32) return launch_pair<MODE_GEMM, EPI_BIAS_GELU_F32, OP_TF32>(tmA, tmB, a, n_clusters, st); break;
+        case EPI_DGELU_F32: if (TF32) return launch_pair<MODE_GEMM, EPI_DGELU_F32, OP_TF32>(tmA, tmB, a, n_clusters, st); break;
     }
     return set_error(LPI_ERR_ARG, "epilogue %d is not available for this operand type", a.epi);
 }
@@ -812,8 +834,9 @@ static int launch_epi_tf32(const CUtensorMap& tmA, const CUtensorMap& tmB, const
 
 using namespace lpi;
 
-static int gemm_entry(bool tf32, const void* A, const void* B, int M, int N, int K, int epi, const void* bias, const void* resid,
+static int gemm_entry(int op, const void* A, const void* B, int M, int N, int K, int epi, const void* bias, const void* resid,
                       void* out, void* out2, const void* aux, int ldo, int tile_n, void* stream) {
+    const bool tf32 = op == OP_TF32;
     const int bke = tf32 ? 32 : BK;
     if (M <= 0 || N <= 0 || K <= 0) return set_error(LPI_ERR_ARG, "gemm: empty problem %dx%dx%d", M, N, K);
     if (K % bke) return set_error(LPI_ERR_ARG, "gemm: K=%d must be a multiple of %d", K, bke);
@@ -837,7 +860,7 @@ static int gemm_entry(bool tf32, const void* A, const void* B, int M, int N, int
     if (bn != 128 && bn != 256 && bn != 512) return set_error(LPI_ERR_ARG, "gemm: tile_n must be 0, 128, 256 or 512 (CTA pair)");
     if (N % (pair ? 256 : bn)) return set_error(LPI_ERR_ARG, "gemm: N=%d not a multiple of the tile width (tile_n=%d)", N, bn);
     CUtensorMap tmA, tmB;
-    const CUtensorMapDataType dt = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    const CUtensorMapDataType dt = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : (op == OP_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
     const int eb = tf32 ? 4 : 2;
     if (int rc = make_tmap_2d(&tmA, A, dt, eb, M, K, K, BM, bke)) return rc;
     if (int rc = make_tmap_2d(&tmB, B, dt, eb, N, K, K, pair ? 128 : bn, bke)) return rc;
@@ -861,8 +884,10 @@ static int gemm_entry(bool tf32, const void* A, const void* B, int M, int N, int
     if (pair) {
         const long ctiles = long(((M + BM - 1) / BM + 1) / 2) * (N / 256);
         const int n_clusters = int(ctiles < sms / 2 ? ctiles : sms / 2);
-        return tf32 ? launch_pair_epi<true>(tmA, tmB, a, n_clusters, st) : launch_pair_epi<false>(tmA, tmB, a, n_clusters, st);
+        return tf32 ? launch_pair_epi<OP_TF32>(tmA, tmB, a, n_clusters, st)
+                    : (op == OP_F16 ? launch_pair_epi<OP_F16>(tmA, tmB, a, n_clusters, st) : launch_pair_epi<OP_BF16>(tmA, tmB, a, n_clusters, st));
     }
+    if (op == OP_F16) return set_error(LPI_ERR_UNSUPPORTED, "gemm_f16: N=%d must be a multiple of 256 (CTA-pair tiles only)", N);
     const long tiles = long((M + BM - 1) / BM) * (N / bn);
     const int grid = int(tiles < sms ? tiles : sms);
     if (tf32) return bn == 256 ? launch_epi_tf32<256>(tmA, tmB, a, grid, st) : launch_epi_tf32<128>(tmA, tmB, a, grid, st);
@@ -873,12 +898,20 @@ extern "C" int lpi_gemm_bf16(const void* A, const void* B, int M, int N, int K, 
                              void* out2, const void* aux, int ldo, int tile_n, void* stream) {
     if (epi == EPI_BIAS_GELU_F32 || epi == EPI_DGELU_F32)
         return set_error(LPI_ERR_ARG, "gemm_bf16: epilogue %d is only available for TF32 operands", epi);
-    return gemm_entry(false, A, B, M, N, K, epi, bias, resid, out, out2, aux, ldo, tile_n, stream);
+    return gemm_entry(OP_BF16, A, B, M, N, K, epi, bias, resid, out, out2, aux, ldo, tile_n, stream);
 }
 
 extern "C" int lpi_gemm_tf32(const void* A, const void* B, int M, int N, int K, int epi, const void* bias, const void* resid, void* out,
                              void* out2, const void* aux, int ldo, int tile_n, void* stream) {
-    return gemm_entry(true, A, B, M, N, K, epi, bias, resid, out, out2, aux, ldo, tile_n, stream);
+    return gemm_entry(OP_TF32, A, B, M, N, K, epi, bias, resid, out, out2, aux, ldo, tile_n, stream);
+}
+
+extern "C" int lpi_gemm_f16(const void* A, const void* B, int M, int N, int K, int epi, const void* bias, const void* resid, void* out,
+                            void* out2, const void* aux, int ldo, int tile_n, void* stream) {
+    if (epi == EPI_BIAS_GELU_F32 || epi == EPI_DGELU_F32)
+        return set_error(LPI_ERR_ARG, "gemm_f16: epilogue %d is only available for TF32 operands", epi);
+    if (tile_n != 0 && tile_n != 512) return set_error(LPI_ERR_ARG, "gemm_f16: only the CTA-pair tile (tile_n 0 or 512) is built");
+    return gemm_entry(OP_F16, A, B, M, N, K, epi, bias, resid, out, out2, aux, ldo, tile_n, stream);
 }
 
 static bool scorer_pair_enabled() {
@@ -939,7 +972,7 @@ extern "C" int lpi_sim_topk_bf16(const void* Q, const void* G, int n_queries, in
     if (pair) {
         const long items = long(((n_queries + BM - 1) / BM + 1) / 2) * n_chunks;
         const int n_clusters = int(items < sms / 2 ? items : sms / 2);
-        return launch_pair<MODE_TOPK, EPI_F32, false>(tmA, tmB, a, n_clusters, static_cast<cudaStream_t>(stream));
+        return launch_pair<MODE_TOPK, EPI_F32, OP_BF16>(tmA, tmB, a, n_clusters, static_cast<cudaStream_t>(stream));
     }
     const long items = long((n_queries + BM - 1) / BM) * n_chunks;
     const int grid = int(items < sms ? items : sms);

@@ -21,8 +21,8 @@ int make_tmap_2d(CUtensorMap* m, const void* ptr, CUtensorMapDataType dt, int el
 
 // tcgen05 attention (attention_tc.cu); L <= 256
 bool attn_tc_enabled(int L);
-int attn_fwd_tc(const void* qkv, void* out, float* out_f32, float* lse2, int B, int L, int H, int causal, cudaStream_t st);
+int attn_fwd_tc(const void* qkv, void* out, float* out_f32, float* lse2, int B, int L, int H, int causal, bool f16, cudaStream_t st);
 int attn_bwd_tc(const void* qkv, const void* d_out, const float* lse2, const float* delta, void* dqkv, float* dqkv_f32, int B, int L, int H,
-                int causal, cudaStream_t st);
+                int causal, bool f16, cudaStream_t st);
 
 }  // namespace lpi

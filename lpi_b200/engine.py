@@ -48,16 +48,21 @@ def _f32(t: torch.Tensor, dev) -> torch.Tensor:
     return t.detach().to(dev, torch.float32).contiguous()
 
 
-def load_blocks(sd: Dict[str, torch.Tensor], prefix: str, dev, need_grad: bool = True, tf32: bool = False) -> List[BlockWeights]:
+def _half(t: torch.Tensor, dev, dtype) -> torch.Tensor:
+    return t.detach().to(dev, torch.float32).to(dtype).contiguous()
+
+
+def load_blocks(sd: Dict[str, torch.Tensor], prefix: str, dev, need_grad: bool = True, tf32: bool = False,
+                half_dtype=torch.bfloat16) -> List[BlockWeights]:
     """`prefix` = 'visual.transformer.resblocks.' or 'transformer.resblocks.' in a CLIP state_dict.  tf32: keep the GEMM
-    weights in fp32 (operands of lpi_gemm_tf32) instead of bf16."""
+    weights in fp32 (operands of lpi_gemm_tf32); otherwise they are stored in `half_dtype` (bf16, or fp16 for lpi_gemm_f16)."""
     blocks = []
     i = 0
     while f"{prefix}{i}.ln_1.weight" in sd:
         p = f"{prefix}{i}."
         g = lambda k: sd[p + k]
         def pair(k):
-            w = _f32(g(k), dev) if tf32 else _bf16(g(k), dev)
+            w = _f32(g(k), dev) if tf32 else _half(g(k), dev, half_dtype)
             return w, (w.t().contiguous() if need_grad else None)
         w_in, w_in_t = pair("attn.in_proj_weight")
         w_out, w_out_t = pair("attn.out_proj.weight")
@@ -95,10 +100,14 @@ class Tower:
     """12 pre-LN residual attention blocks (model.py:187-196) over a [B*L, D] fp32 residual stream."""
 
     def __init__(self, sd, prefix: str, heads: int, causal: bool, dev, need_grad: bool = True, precision: str = "bf16"):
-        if precision not in ("bf16", "tf32"):
-            raise ValueError(f"precision must be 'bf16' or 'tf32', got {precision!r}")
+        if precision not in ("bf16", "tf32", "fp16"):
+            raise ValueError(f"precision must be 'bf16', 'fp16' or 'tf32', got {precision!r}")
         self.tf32 = precision == "tf32"
-        self.blocks = load_blocks(sd, prefix, dev, need_grad, self.tf32)
+        self.half = torch.float16 if precision == "fp16" else torch.bfloat16      # dtype of GEMM / attention operands and shadows
+        # fp16 gradient path: the 16-bit gradient stream is carried times 2^10 so that small gradients stay in fp16's normal range
+        # (min normal 6.1e-5); every op between two LayerNorm backwards is linear in the gradient, so the factor is exact.
+        self.grad_scale = 1024.0 if precision == "fp16" else None
+        self.blocks = load_blocks(sd, prefix, dev, need_grad, self.tf32, self.half)
         self.heads = heads
         self.causal = causal
         self.width = heads * 64
@@ -115,15 +124,15 @@ class Tower:
         for li, w in enumerate(self.blocks):
             if inject is not None and li != 0 and li in inject["layers"]:
                 ops.inject_prompt_rows(x, inject["table"][:, li].contiguous(), inject["sel"], B, L, inject["P"], self.width)
-            _, h = ops.layernorm_fwd(x, w.ln1_g, w.ln1_b)
+            _, h = ops.layernorm_fwd(x, w.ln1_g, w.ln1_b, half_dtype=self.half)
             qkv = ops.gemm(h, w.w_in, ops.EPI_BIAS_BF16, bias=w.b_in)
             o, lse = ops.attn_fwd(qkv, B, L, H, self.causal, want_lse=tape is not None)
             if tape is not None:
                 x1 = ops.gemm(o, w.w_out, ops.EPI_BIAS_RESID_F32, bias=w.b_out, resid=x)
             else:
                 x1 = ops.gemm(o, w.w_out, ops.EPI_BIAS_RESID_F32, bias=w.b_out, resid=x, out=x)      # in place
-            _, h2 = ops.layernorm_fwd(x1, w.ln2_g, w.ln2_b)
-            z = torch.empty(x.shape[0], 4 * self.width, device=x.device, dtype=torch.bfloat16) if tape is not None else None
+            _, h2 = ops.layernorm_fwd(x1, w.ln2_g, w.ln2_b, half_dtype=self.half)
+            z = torch.empty(x.shape[0], 4 * self.width, device=x.device, dtype=self.half) if tape is not None else None
             a = ops.gemm(h2, w.w_fc, ops.EPI_BIAS_GELU_BF16, bias=w.b_fc, out2=z)
             if tape is not None:
                 x2 = ops.gemm(a, w.w_proj, ops.EPI_BIAS_RESID_F32, bias=w.b_proj, resid=x1)
@@ -176,7 +185,7 @@ class Tower:
     def backward(self, tape: TowerTape, g: torch.Tensor, g_bf16: torch.Tensor, inject: Optional[dict] = None,
                  inject_grads: Optional[dict] = None) -> torch.Tensor:
         """g fp32 [B*L, D] = d loss / d (tower output), updated in place down to d loss / d (tower input);
-        g_bf16 is its bf16 shadow (must match g on entry).  With `inject`, inject_grads[l] receives
+        g_bf16 is its 16-bit shadow (must match g on entry; bf16, or fp16 holding grad_scale * g for an fp16 tower).  With `inject`, inject_grads[l] receives
         sum_b g_l[b, 1:P+1] for every injected layer."""
         B, L, H = tape.B, tape.L, self.heads
         if self.tf32:
@@ -185,11 +194,11 @@ class Tower:
             w, s = self.blocks[li], tape.blocks[li]
             dz = ops.gemm(g_bf16, w.w_proj_t, ops.EPI_DGELU_BF16, aux=s.z)
             dh2 = ops.gemm(dz, w.w_fc_t, ops.EPI_F32)
-            ops.layernorm_bwd(dh2, s.x1, w.ln2_g, g, g_bf16, accumulate=True)
+            ops.layernorm_bwd(dh2, s.x1, w.ln2_g, g, g_bf16, accumulate=True, grad_scale=self.grad_scale)
             do = ops.gemm(g_bf16, w.w_out_t, ops.EPI_BF16)
             dqkv = ops.attn_bwd(s.qkv, s.o, do, s.lse, B, L, H, self.causal)
             dh1 = ops.gemm(dqkv, w.w_in_t, ops.EPI_F32)
-            ops.layernorm_bwd(dh1, s.x, w.ln1_g, g, g_bf16, accumulate=True)
+            ops.layernorm_bwd(dh1, s.x, w.ln1_g, g, g_bf16, accumulate=True, grad_scale=self.grad_scale)
             if inject is not None and li != 0 and li in inject["layers"] and inject_grads is not None:
                 n_tables = inject["table"].shape[0]
                 inject_grads[li] = ops.sum_prompt_rows(g, inject["sel"], B, L, inject["P"], n_tables, self.width)
@@ -243,9 +252,9 @@ class VisionEngine:
         B, L, D, P = tape["B"], tape["L"], self.width, tape["P"]
         dev = tape["x"].device
         g = torch.zeros(B * L, D, device=dev, dtype=torch.float32)
-        gb = torch.zeros(B * L, D, device=dev, dtype=torch.bfloat16)
+        gb = torch.zeros(B * L, D, device=dev, dtype=self.tower.half)
         ops.head_bwd(None if dfeat is None else dfeat.contiguous(), None if dz is None else dz.contiguous(), tape["z"], tape["x"],
-                     tape["rows"], self.ln_post[0], self.proj, g, gb)
+                     tape["rows"], self.ln_post[0], self.proj, g, gb, grad_scale=self.tower.grad_scale)
         inj_grads = {}
         self.tower.backward(tape["tower"], g, gb, tape["inject"], inj_grads)
         if P == 0:
@@ -261,10 +270,12 @@ class VisionEngine:
 class TextEngine:
     """PromptLearner splice + TextEncoder.forward (prompt_learner.py:133-163, 52-63) on the kernels."""
 
-    def __init__(self, sd: Dict[str, torch.Tensor], dev, need_grad: bool = True, precision: str = "tf32"):
-        """precision 'tf32' (default): the text tower's GEMMs run on fp32 operands / TF32 tensor cores -- with bf16 operands the
-        text-side prompt gradients sit at the 2e-2 parity limit (measured 2.1-2.2e-2), and the text tower
-        is only 13.5 % of the step FLOPs.  'bf16' is available for throughput studies."""
+    def __init__(self, sd: Dict[str, torch.Tensor], dev, need_grad: bool = True, precision: str = "fp16"):
+        """precision 'fp16' (default): fp16 GEMM / attention operands with fp32 accumulation -- the 10-bit mantissa the text tower needs
+        (with bf16 operands the text-side prompt gradients sit at the 2e-2 parity limit, measured 2.1-2.2e-2)
+        at the full kind::f16 tensor rate; it is also the reference's own GPU dtype (convert_weights, model.py:394-415).  The fp16
+        gradient stream is scaled by 2^10 (Tower.grad_scale).  'tf32' = fp32 operands on the half-rate TF32 path (same mantissa,
+        twice the bytes; the round-1 default before the fp16 kernels existed), 'bf16' for throughput studies."""
         self.emb = _f32(sd["token_embedding.weight"], dev)
         self.pos = _f32(sd["positional_embedding"], dev)
         self.ln_final = (_f32(sd["ln_final.weight"], dev), _f32(sd["ln_final.bias"], dev))
@@ -299,9 +310,9 @@ class TextEngine:
         B, L, D, P = tape["B"], tape["L"], self.width, tape["P"]
         dev = tape["x"].device
         g = torch.zeros(B * L, D, device=dev, dtype=torch.float32)
-        gb = torch.zeros(B * L, D, device=dev, dtype=torch.bfloat16)
+        gb = torch.zeros(B * L, D, device=dev, dtype=self.tower.half)
         ops.head_bwd(None if dfeat is None else dfeat.contiguous(), None if dz is None else dz.contiguous(), tape["z"], tape["x"],
-                     tape["rows"], self.ln_final[0], self.proj, g, gb)
+                     tape["rows"], self.ln_final[0], self.proj, g, gb, grad_scale=self.tower.grad_scale)
         inj_grads = {}
         self.tower.backward(tape["tower"], g, gb, tape["inject"], inj_grads)
         if P == 0:
@@ -335,9 +346,9 @@ class TextEngine:
         B, L, D = tape["B"], tape["L"], self.width
         dev = tape["x"].device
         g = torch.zeros(B * L, D, device=dev, dtype=torch.float32)
-        gb = torch.zeros(B * L, D, device=dev, dtype=torch.bfloat16)
+        gb = torch.zeros(B * L, D, device=dev, dtype=self.tower.half)
         ops.head_bwd(None if dfeat is None else dfeat.contiguous(), None if dz is None else dz.contiguous(), tape["z"], tape["x"],
-                     tape["rows"], self.ln_final[0], self.proj, g, gb)
+                     tape["rows"], self.ln_final[0], self.proj, g, gb, grad_scale=self.tower.grad_scale)
         inj_grads = {}
         self.tower.backward(tape["tower"], g, gb, tape["inject"], inj_grads)
         G = None

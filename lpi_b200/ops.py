@@ -34,24 +34,28 @@ def _chk(t: torch.Tensor, dtype, name: str):
 def gemm(a: torch.Tensor, w: torch.Tensor, epi: int, bias: Optional[torch.Tensor] = None,
          resid: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, out2: Optional[torch.Tensor] = None,
          aux: Optional[torch.Tensor] = None, tile_n: int = 0) -> torch.Tensor:
-    """out[M,N] = epilogue(a[M,K] @ w[N,K]^T).  a, w bf16.  See enum lpi_epilogue in include/lpi_b200.h."""
+    """out[M,N] = epilogue(a[M,K] @ w[N,K]^T).  a, w both bf16 (lpi_gemm_bf16) or both fp16 (lpi_gemm_f16; every 16-bit
+    output / out2 / aux is then fp16 too).  See enum lpi_epilogue in include/lpi_b200.h."""
     _lib.require_device()
-    _chk(a, torch.bfloat16, "a")
-    _chk(w, torch.bfloat16, "w")
+    h = a.dtype
+    if h not in (torch.bfloat16, torch.float16):
+        raise _lib.LpiError(f"a must be bf16 or fp16, got {a.dtype}")
+    _chk(a, h, "a")
+    _chk(w, h, "w")
     M, K = a.shape
     N = w.shape[0]
     assert w.shape[1] == K
     f32_out = epi in (EPI_BIAS_RESID_F32, EPI_F32, EPI_ACC_F32, EPI_BIAS_F32)
     if out is None:
-        out = torch.empty(M, N, device=a.device, dtype=torch.float32 if f32_out else torch.bfloat16)
-    _chk(out, torch.float32 if f32_out else torch.bfloat16, "out")
+        out = torch.empty(M, N, device=a.device, dtype=torch.float32 if f32_out else h)
+    _chk(out, torch.float32 if f32_out else h, "out")
     for t, n in ((bias, "bias"), (resid, "resid")):
         if t is not None:
             _chk(t, torch.float32, n)
     for t, n in ((out2, "out2"), (aux, "aux")):
         if t is not None:
-            _chk(t, torch.bfloat16, n)
-    call("gemm_bf16", ptr(a), ptr(w), M, N, K, epi, ptr(bias), ptr(resid), ptr(out), ptr(out2), ptr(aux),
+            _chk(t, h, n)
+    call("gemm_f16" if h == torch.float16 else "gemm_bf16", ptr(a), ptr(w), M, N, K, epi, ptr(bias), ptr(resid), ptr(out), ptr(out2), ptr(aux),
          out.stride(0), tile_n, stream_ptr())
     _count()
     return out
@@ -177,12 +181,21 @@ def l2_normalize(x: torch.Tensor, want_norm: bool = False):
 
 # ------------------------------------------------------------------------------------------ attention
 def attn_fwd(qkv: torch.Tensor, B: int, L: int, H: int, causal: bool, want_lse: bool = True, want_f32: bool = False):
-    """qkv [B*L, 3*H*64] bf16 -> (out [B*L, H*64] bf16, lse2 [B*H*L] fp32 or None[, out_f32])."""
+    """qkv [B*L, 3*H*64] bf16 or fp16 -> (out [B*L, H*64] same dtype, lse2 [B*H*L] fp32 or None[, out_f32])."""
     _lib.require_device()
-    _chk(qkv, torch.bfloat16, "qkv")
+    h = qkv.dtype
+    if h not in (torch.bfloat16, torch.float16):
+        raise _lib.LpiError(f"qkv must be bf16 or fp16, got {qkv.dtype}")
+    _chk(qkv, h, "qkv")
     assert qkv.shape == (B * L, 3 * H * 64)
-    out = torch.empty(B * L, H * 64, device=qkv.device, dtype=torch.bfloat16)
+    out = torch.empty(B * L, H * 64, device=qkv.device, dtype=h)
     lse = torch.empty(B * H * L, device=qkv.device, dtype=torch.float32) if want_lse else None
+    if h == torch.float16:
+        if want_f32:
+            raise _lib.LpiError("attn_fwd: the fp16 path has no fp32 hand-over")
+        call("attn_fwd_f16", ptr(qkv), ptr(out), ptr(lse), B, L, H, int(causal), stream_ptr())
+        _count()
+        return out, lse
     of = torch.empty(B * L, H * 64, device=qkv.device, dtype=torch.float32) if want_f32 else None
     call("attn_fwd", ptr(qkv), ptr(out), ptr(of), ptr(lse), B, L, H, int(causal), stream_ptr())
     _count()
@@ -190,15 +203,24 @@ def attn_fwd(qkv: torch.Tensor, B: int, L: int, H: int, causal: bool, want_lse: 
 
 
 def attn_bwd(qkv, out, d_out, lse, B: int, L: int, H: int, causal: bool, dqkv: Optional[torch.Tensor] = None, f32: bool = False):
+    h = qkv.dtype
     for t, n in ((qkv, "qkv"), (out, "out"), (d_out, "d_out")):
-        _chk(t, torch.bfloat16, n)
+        _chk(t, h, n)
     _chk(lse, torch.float32, "lse")
+    delta = torch.empty(B * H * L, device=qkv.device, dtype=torch.float32)
+    if h == torch.float16:
+        if f32:
+            raise _lib.LpiError("attn_bwd: the fp16 path writes fp16 gradients")
+        if dqkv is None:
+            dqkv = torch.empty_like(qkv)
+        call("attn_bwd_f16", ptr(qkv), ptr(out), ptr(d_out), ptr(lse), ptr(delta), ptr(dqkv), B, L, H, int(causal), stream_ptr())
+        _count(2)
+        return dqkv
     if dqkv is None:
         dqkv = torch.empty_like(qkv, dtype=torch.float32 if f32 else torch.bfloat16)
-    delta = torch.empty(B * H * L, device=qkv.device, dtype=torch.float32)
     call("attn_bwd", ptr(qkv), ptr(out), ptr(d_out), ptr(lse), ptr(delta), None if f32 else ptr(dqkv), ptr(dqkv) if f32 else None, B, L, H,
          int(causal), stream_ptr())
-    _count(3)
+    _count(2 if L <= 256 else 3)
     return dqkv
 
 
@@ -206,24 +228,35 @@ def attn_bwd(qkv, out, d_out, lse, B: int, L: int, H: int, causal: bool, dqkv: O
 LN_EPS = 1e-5
 
 
-def layernorm_fwd(x, gamma, beta, want_f32=False, want_bf16=True):
+def layernorm_fwd(x, gamma, beta, want_f32=False, want_bf16=True, half_dtype=torch.bfloat16):
+    """-> (fp32 copy or None, 16-bit shadow (bf16, or fp16 with half_dtype=torch.float16) or None)"""
     _lib.require_device()
     _chk(x, torch.float32, "x")
     M, D = x.shape
     of = torch.empty_like(x) if want_f32 else None
-    ob = torch.empty(M, D, device=x.device, dtype=torch.bfloat16) if want_bf16 else None
-    call("layernorm_fwd", ptr(x), ptr(gamma), ptr(beta), ptr(of), ptr(ob), C.c_longlong(M), D, C.c_float(LN_EPS), stream_ptr())
+    ob = torch.empty(M, D, device=x.device, dtype=half_dtype) if want_bf16 else None
+    call("layernorm_fwd_f16" if half_dtype == torch.float16 else "layernorm_fwd", ptr(x), ptr(gamma), ptr(beta), ptr(of), ptr(ob),
+         C.c_longlong(M), D, C.c_float(LN_EPS), stream_ptr())
     _count()
     return of, ob
 
 
-def layernorm_bwd(dy, x, gamma, g, g_bf16=None, accumulate=True):
-    """g = (accumulate ? g : 0) + dLN(dy; x, gamma), in place; optional bf16 shadow."""
+def layernorm_bwd(dy, x, gamma, g, g_bf16=None, accumulate=True, grad_scale: Optional[float] = None):
+    """g = (accumulate ? g : 0) + dLN(dy; x, gamma), in place; optional 16-bit shadow.  With grad_scale (fp16 gradient path):
+    dy is grad_scale * (true dy), g stays true scale, the fp16 shadow is grad_scale * g."""
     for t, n in ((dy, "dy"), (x, "x"), (g, "g")):
         _chk(t, torch.float32, n)
     M, D = x.shape
-    call("layernorm_bwd", ptr(dy), ptr(x), ptr(gamma), ptr(g), ptr(g_bf16), C.c_longlong(M), D, C.c_float(LN_EPS), int(accumulate),
-         stream_ptr())
+    if grad_scale is not None:
+        if g_bf16 is not None:
+            _chk(g_bf16, torch.float16, "g_f16")
+        call("layernorm_bwd_f16", ptr(dy), ptr(x), ptr(gamma), ptr(g), ptr(g_bf16), C.c_longlong(M), D, C.c_float(LN_EPS), int(accumulate),
+             C.c_float(grad_scale), stream_ptr())
+    else:
+        if g_bf16 is not None:
+            _chk(g_bf16, torch.bfloat16, "g_bf16")
+        call("layernorm_bwd", ptr(dy), ptr(x), ptr(gamma), ptr(g), ptr(g_bf16), C.c_longlong(M), D, C.c_float(LN_EPS), int(accumulate),
+             stream_ptr())
     _count()
     return g
 
@@ -285,19 +318,26 @@ def head_fwd(x, row_idx, ln_g, ln_b, proj):
     z = torch.empty(B, E, device=x.device, dtype=torch.float32)
     f = torch.empty(B, E, device=x.device, dtype=torch.float32)
     call("head_fwd", ptr(x), ptr(row_idx), ptr(ln_g), ptr(ln_b), ptr(proj), ptr(z), ptr(f), B, D, E, C.c_float(LN_EPS), stream_ptr())
-    _count()
+    _count(2)
     return f, z
 
 
-def head_bwd(dfeat, dz, z, x, row_idx, ln_g, proj, g, g_bf16=None):
+def head_bwd(dfeat, dz, z, x, row_idx, ln_g, proj, g, g_bf16=None, grad_scale: Optional[float] = None):
+    """Rows row_idx of g are assigned; g_bf16 = optional 16-bit shadow (fp16 scaled by grad_scale when grad_scale is given)."""
     for t, n in ((dfeat, "dfeat"), (dz, "dz")):
         if t is not None:
             _chk(t, torch.float32, n)
     B = row_idx.shape[0]
     D, E = proj.shape
-    call("head_bwd", ptr(dfeat), ptr(dz), ptr(z), ptr(x), ptr(row_idx), ptr(ln_g), ptr(proj), ptr(g), ptr(g_bf16), B, D, E, C.c_float(LN_EPS),
-         stream_ptr())
-    _count()
+    if grad_scale is not None:
+        if g_bf16 is not None:
+            _chk(g_bf16, torch.float16, "g_f16")
+        call("head_bwd_f16", ptr(dfeat), ptr(dz), ptr(z), ptr(x), ptr(row_idx), ptr(ln_g), ptr(proj), ptr(g), ptr(g_bf16), C.c_float(grad_scale),
+             B, D, E, C.c_float(LN_EPS), stream_ptr())
+    else:
+        call("head_bwd", ptr(dfeat), ptr(dz), ptr(z), ptr(x), ptr(row_idx), ptr(ln_g), ptr(proj), ptr(g), ptr(g_bf16), B, D, E,
+             C.c_float(LN_EPS), stream_ptr())
+    _count(2)
 
 
 # ------------------------------------------------------------------------------------------ DecomposedPrompt

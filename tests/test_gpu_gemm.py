@@ -8,13 +8,13 @@ from lpi_b200 import ops
 pytestmark = pytest.mark.gpu
 
 
-def _case(M, N, K, epi, tile_n, seed=0):
+def _case(M, N, K, epi, tile_n, seed=0, half=torch.bfloat16):
     g = torch.Generator().manual_seed(seed)
-    a = torch.randn(M, K, generator=g).cuda().bfloat16()
-    w = (torch.randn(N, K, generator=g) * K ** -0.5).cuda().bfloat16()
+    a = torch.randn(M, K, generator=g).cuda().to(half)
+    w = (torch.randn(N, K, generator=g) * K ** -0.5).cuda().to(half)
     bias = torch.randn(N, generator=g).cuda()
     resid = torch.randn(M, N, generator=g).cuda()
-    aux = torch.randn(M, N, generator=g).cuda().bfloat16()
+    aux = torch.randn(M, N, generator=g).cuda().to(half)
     ref = a.float() @ w.float().t()
     kw, second = {}, None
     if epi == ops.EPI_BIAS_BF16:
@@ -22,11 +22,11 @@ def _case(M, N, K, epi, tile_n, seed=0):
     elif epi == ops.EPI_BIAS_GELU_BF16:
         z = ref + bias
         want = z * torch.sigmoid(1.702 * z)
-        kw = dict(bias=bias, out2=torch.empty(M, N, device="cuda", dtype=torch.bfloat16))
+        kw = dict(bias=bias, out2=torch.empty(M, N, device="cuda", dtype=half))
         second = (kw["out2"], z)
     elif epi == ops.EPI_BIAS_RESID_F32:
         want = resid + ref + bias
-        kw = dict(bias=bias, resid=resid, out2=torch.empty(M, N, device="cuda", dtype=torch.bfloat16))
+        kw = dict(bias=bias, resid=resid, out2=torch.empty(M, N, device="cuda", dtype=half))
         second = (kw["out2"], want)
     elif epi == ops.EPI_F32:
         want = ref
@@ -42,10 +42,11 @@ def _case(M, N, K, epi, tile_n, seed=0):
         want = ref
     out = ops.gemm(a, w, epi, tile_n=tile_n, **kw)
     scale = max(1.0, want.abs().max().item())
-    tol = (2 ** -8 if out.dtype == torch.bfloat16 else 2e-5) * scale      # bf16 rounding / fp32 accumulation order
+    hr = 2 ** -8 if half == torch.bfloat16 else 2 ** -10               # output rounding of the 16-bit type (+ fast-sigmoid error)
+    tol = (hr if out.dtype == half else 2e-5) * scale                   # 16-bit rounding / fp32 accumulation order
     assert (out.float() - want).abs().max().item() <= tol
     if second is not None:
-        assert (second[0].float() - second[1]).abs().max().item() <= 2 ** -8 * max(1.0, second[1].abs().max().item())
+        assert (second[0].float() - second[1]).abs().max().item() <= hr * max(1.0, second[1].abs().max().item())
 
 
 @pytest.mark.parametrize("M,N,K", [(100, 128, 64), (300, 512, 512), (4928, 1536, 512), (13632, 2304, 768),
@@ -63,6 +64,23 @@ def test_gemm_epilogues(epi):
     _case(333, 512, 2048, epi, 128, seed=1)
     _case(1000, 768, 768, epi, 512, seed=2)          # CTA-pair kernel (cta_group::2), odd number of M tiles
     _case(13632, 768, 3072, epi, 512, seed=3)
+
+
+@pytest.mark.parametrize("epi", range(8))
+def test_gemm_f16_epilogues(epi):
+    """fp16 operands (text tower): same epilogues, every 16-bit tensor is fp16, tolerance = fp16 output rounding."""
+    _case(1000, 768, 768, epi, 0, seed=4, half=torch.float16)
+    _case(4928, 512, 2048, epi, 0, seed=5, half=torch.float16)
+    _case(4928, 1536, 512, epi, 512, seed=6, half=torch.float16)
+
+
+def test_gemm_f16_rejects_narrow_n():
+    from lpi_b200._lib import LpiError
+
+    a = torch.zeros(64, 64, device="cuda", dtype=torch.float16)
+    w = torch.zeros(128, 64, device="cuda", dtype=torch.float16)
+    with pytest.raises(LpiError):
+        ops.gemm(a, w, ops.EPI_F32)
 
 
 def test_gemm_rejects_bad_shapes():

@@ -80,6 +80,47 @@ def test_attention_fwd_bwd(B, L, H, causal):
             assert _rel(dqkv[:, sl].float(), qr.grad[:, sl]) < 3e-2, part
 
 
+@pytest.mark.parametrize("B,L,H,causal", [(3, 77, 8, True), (2, 213, 12, False), (1, 16, 1, False), (2, 130, 3, True)])
+def test_attention_fp16(B, L, H, causal):
+    """fp16 storage (text tower): tighter than bf16 (P, dS and the outputs carry 10 mantissa bits); the backward is linear in d_out,
+    so scaling d_out by 2^10 (the engine's gradient scale) scales dqkv by exactly 2^10."""
+    g = torch.Generator().manual_seed(L * 17 + H)
+    D = H * 64
+    qkv = (torch.randn(B * L, 3 * D, generator=g) * 1.5).cuda().half()
+    out, lse = ops.attn_fwd(qkv, B, L, H, causal)
+    qr = qkv.float().requires_grad_(True)
+    ref, s = _ref_attention(qr, B, L, H, causal)
+    assert out.dtype == torch.float16 and (out.float() - ref).abs().max() < 4e-3 * ref.abs().max()
+    want_lse = torch.logsumexp(s, -1) * math.log2(math.e)
+    assert (lse.view(B, H, L) - want_lse).abs().max() < 1e-3
+    d_out = (torch.randn(B * L, D, generator=g) * 1e-3).cuda().half()
+    ref.backward(d_out.float())
+    dqkv = ops.attn_bwd(qkv, out, d_out, lse, B, L, H, causal)
+    assert dqkv.dtype == torch.float16
+    d_scaled = (d_out.float() * 1024).half()
+    dq_scaled = ops.attn_bwd(qkv, out, d_scaled, lse, B, L, H, causal)
+    assert _rel(dq_scaled.float() / 1024, qr.grad) < 4e-3              # scaled path: fp16 rounding only
+    assert _rel(dqkv.float(), qr.grad) < 2e-2                          # unscaled 1e-3 gradients already lose bits to fp16 subnormals
+
+
+def test_layernorm_fp16_shadow_and_grad_scale():
+    g = torch.Generator().manual_seed(11)
+    M, D = 333, 512
+    x = torch.randn(M, D, generator=g).cuda() * 3 + 1
+    gamma, beta = (1 + 0.1 * torch.randn(D, generator=g)).cuda(), (0.1 * torch.randn(D, generator=g)).cuda()
+    of, oh = ops.layernorm_fwd(x, gamma, beta, want_f32=True, half_dtype=torch.float16)
+    assert oh.dtype == torch.float16 and torch.equal(of.half(), oh)
+    dy = torch.randn(M, D, generator=g).cuda() * 1e-4
+    xr = x.clone().requires_grad_(True)
+    F.layer_norm(xr, (D,), gamma, beta, 1e-5).backward(dy)
+    base = torch.randn(M, D, generator=g).cuda() * 1e-4
+    gacc = base.clone()
+    gh = torch.empty(M, D, device="cuda", dtype=torch.float16)
+    ops.layernorm_bwd(dy * 1024, x, gamma, gacc, gh, accumulate=True, grad_scale=1024.0)
+    assert (gacc - (base + xr.grad)).abs().max() < 5e-5 * 1e-3
+    assert (gh.float() / 1024 - gacc).abs().max() <= 2 ** -10 * gacc.abs().max()
+
+
 def test_im2col_matches_conv():
     g = torch.Generator().manual_seed(5)
     img = torch.randn(3, 3, 224, 224, generator=g).cuda()

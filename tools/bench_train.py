@@ -1,5 +1,5 @@
 """Times one LPI training step (COCO-shaped, BASELINE.json configs[2]) on one GPU: forward of both towers, three losses,
-backward to the prompt factors, SGD step.  python tools/bench_train.py [--batch 64] [--steps 10] [--text-precision tf32]"""
+backward to the prompt factors, SGD step.  python tools/bench_train.py [--batch 64] [--steps 10] [--text-precision fp16|tf32|bf16]"""
 import argparse
 import json
 import os
@@ -19,7 +19,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--text-precision", default="tf32")
+    ap.add_argument("--text-precision", default="fp16")
     ap.add_argument("--fwd-only", action="store_true")
     a = ap.parse_args()
     dev = torch.device("cuda")
