@@ -43,6 +43,7 @@ struct GemmArgs {
     float* out2_f32;               // [M, ldo] fp32 pre-activation (EPI_BIAS_GELU_F32)
     const float* aux_f32;          // [M, ldo] fp32 pre-activation (EPI_DGELU_F32)
     int ldo;
+    int precise_act;               // fp16 outputs: 1 = ex2 + rcp sigmoid (2 MUFU ops), 0 = tanh.approx (1 MUFU op, |err| <= 2^-12)
     // MODE_TOPK
     int k;                         // top-k (<= TOPK_MAX)
     int n_chunks;                  // gallery split per query tile (load balance)
@@ -226,8 +227,13 @@ __device__ __forceinline__ void epilogue_block(const GemmArgs& p, const float4* 
             for (int i = 0; i < 8; ++i) {
                 const float2 z0 = unpack_h2<F16>(e[i].x);
                 const float2 z1 = unpack_h2<F16>(e[i].y);
-                v[i].x *= quick_gelu_grad<F16>(z0.x); v[i].y *= quick_gelu_grad<F16>(z0.y);
-                v[i].z *= quick_gelu_grad<F16>(z1.x); v[i].w *= quick_gelu_grad<F16>(z1.y);
+                if (F16 && p.precise_act) {
+                    v[i].x *= quick_gelu_grad<true>(z0.x); v[i].y *= quick_gelu_grad<true>(z0.y);
+                    v[i].z *= quick_gelu_grad<true>(z1.x); v[i].w *= quick_gelu_grad<true>(z1.y);
+                } else {
+                    v[i].x *= quick_gelu_grad<false>(z0.x); v[i].y *= quick_gelu_grad<false>(z0.y);
+                    v[i].z *= quick_gelu_grad<false>(z1.x); v[i].w *= quick_gelu_grad<false>(z1.y);
+                }
             }
         }
 #pragma unroll
@@ -236,7 +242,8 @@ __device__ __forceinline__ void epilogue_block(const GemmArgs& p, const float4* 
             const size_t off = base + size_t(i * 4) * p.ldo;
             if (EPI == EPI_BIAS_GELU_BF16) {
                 if (p.out2_bf16) *reinterpret_cast<uint2*>(p.out2_bf16 + off) = make_uint2(pack_h2<F16>(v[i].x, v[i].y), pack_h2<F16>(v[i].z, v[i].w));
-                v[i] = make_float4(quick_gelu<F16>(v[i].x), quick_gelu<F16>(v[i].y), quick_gelu<F16>(v[i].z), quick_gelu<F16>(v[i].w));
+                if (F16 && p.precise_act) v[i] = make_float4(quick_gelu<true>(v[i].x), quick_gelu<true>(v[i].y), quick_gelu<true>(v[i].z), quick_gelu<true>(v[i].w));
+                else v[i] = make_float4(quick_gelu<false>(v[i].x), quick_gelu<false>(v[i].y), quick_gelu<false>(v[i].z), quick_gelu<false>(v[i].w));
             }
             *reinterpret_cast<uint2*>(p.out_bf16 + off) = make_uint2(pack_h2<F16>(v[i].x, v[i].y), pack_h2<F16>(v[i].z, v[i].w));
         }
@@ -866,6 +873,14 @@ static int gemm_entry(int op, const void* A, const void* B, int M, int N, int K,
     if (int rc = make_tmap_2d(&tmB, B, dt, eb, N, K, K, pair ? 128 : bn, bke)) return rc;
     GemmArgs a{};
     a.M = M; a.N = N; a.K = K; a.epi = epi; a.ldo = ldo;
+    {
+        static int precise = -1;
+        if (precise < 0) {
+            const char* e = getenv("LPI_F16_PRECISE_ACT");
+            precise = (e && e[0] == '1') ? 1 : 0;
+        }
+        a.precise_act = precise;
+    }
     a.bias = static_cast<const float*>(bias);
     a.resid = static_cast<const float*>(resid);
     if (epi == EPI_DGELU_F32) a.aux_f32 = static_cast<const float*>(aux);
