@@ -491,7 +491,11 @@ struct PairCfg {
     static constexpr int RING_OFF = (MODE == MODE_GEMM) ? 0 : A_RESIDENT_KB * A_BYTES;
     static constexpr int BAR_OFF = RING_OFF + STAGES * STAGE_BYTES;
     static constexpr int LIST_OFF = BAR_OFF + 256;
-    static constexpr int TAIL = (BM * TOPK_MAX * 8 > 4 * 32 * 32 * 4) ? BM * TOPK_MAX * 8 : 4 * 32 * 32 * 4;
+    // MODE_GEMM runs EIGHT epilogue warps (two per TMEM lane quadrant, each draining half of the 256 accumulator columns): with four,
+    // the GELU / dGELU / residual epilogues of the K = 768 GEMMs took ~2x their 48-MMA main loop (95 us for a 46 us GEMM)
+    static constexpr int EPI_WARPS = (MODE == MODE_GEMM) ? 8 : 4;
+    static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+    static constexpr int TAIL = (MODE == MODE_GEMM) ? EPI_WARPS * 32 * 32 * 4 : BM * TOPK_MAX * 8;
     static constexpr int SMEM_BYTES = LIST_OFF + TAIL + 1024;
     static constexpr int TMEM_COLS = 512;
 };
@@ -499,7 +503,7 @@ struct PairCfg {
 enum { OP_BF16 = 0, OP_TF32 = 1, OP_F16 = 2 };      // operand type of the CTA-pair GEMM
 
 template <int MODE, int EPI, int OP>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(PairCfg<MODE>::THREADS, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs p) {
     using C = PairCfg<MODE>;
     constexpr bool TF32 = OP == OP_TF32;
@@ -538,7 +542,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             for (int a = 0; a < 2; ++a) {
                 mbar_init(tfull_bar(a), 1);      // multicast commit
-                mbar_init(tempty_bar(a), 8);     // 4 epilogue warps x 2 CTAs (only the leader's copy is used)
+                mbar_init(tempty_bar(a), 2 * C::EPI_WARPS);     // every epilogue warp of both CTAs (only the leader's copy is used)
             }
             mbar_init(afull_bar, 1);
             mbar_init(aempty_bar, 1);
@@ -636,8 +640,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
         }
     } else {
-        // ------------------------------------------------------------ epilogue warps (2..5) of BOTH CTAs: own 128 rows
+        // ------------------------------------------------------------ epilogue warps (2..) of BOTH CTAs: own 128 rows;
+        // MODE_GEMM: warps 2..5 drain columns [0, 128), warps 6..9 columns [128, 256) of the same lane quadrants
         const int quad = warp & 3;
+        const int col_half = (warp - 2) >> 2;                  // 0 for the first four epilogue warps
         const int r_local = quad * 32 + lane;
         int acc = 0;
         uint32_t acc_phase = 0;
@@ -659,7 +665,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 tc_fence_after();
                 if (MODE == MODE_GEMM) {
 #pragma unroll 1
-                    for (int c = 0; c < BN / 32; ++c) {
+                    for (int c = col_half * (BN / 64); c < (col_half + 1) * (BN / 64); ++c) {
                         uint32_t r[32];
                         const uint32_t taddr = tmem_base + uint32_t(acc * BN + c * 32) + (uint32_t(quad * 32) << 16);
                         LPI_TMEM_LD_X32(taddr, r);
@@ -776,7 +782,7 @@ static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * n_clusters);
-    cfg.blockDim = dim3(GEMM_THREADS);
+    cfg.blockDim = dim3(PairCfg<MODE>::THREADS);
     cfg.dynamicSmemBytes = PairCfg<MODE>::SMEM_BYTES;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
