@@ -134,15 +134,66 @@ class SPrompts(object):
             raise LpiError("pass task_loaders=[(train_loader, test_loader), ...]: the COCO file datasets of the reference "
                            "(utils/data.py) are outside the hot path (SURVEY.md section 8(f) f4)")
         final_res = {}
-        for i in range(min(self.n_tasks, len(task_loaders))):
+        start = 0
+        resume = self.args.get("resume_from")
+        if resume:
+            final_res = self.load_checkpoint(resume)
+            start = self.cur_id + 1
+            self.log.info("resumed after task %d from %s", self.cur_id, resume)
+        ckpt_dir = self.args.get("checkpoint_dir")
+        for i in range(start, min(self.n_tasks, len(task_loaders))):
             self._cur_task = [i]
             self.cur_id = i
             self._network.update_fc(self._total_classes)
             self.train_loader, self.test_loader = task_loaders[i]
             final_res[i] = self._train(self.train_loader, self.test_loader)
+            if ckpt_dir:
+                os.makedirs(ckpt_dir, exist_ok=True)
+                self.save_checkpoint(os.path.join(ckpt_dir, f"task_{i}.pt"), final_res)
         os.makedirs("./res", exist_ok=True)
         self.save_dict(final_res, f"./res/{datetime.now()}.json")
         return final_res
+
+    # ------------------------------------------------------------------ per-task checkpoint / resume
+    def checkpoint_state(self, results: Optional[dict] = None) -> dict:
+        """Everything a continual run needs to continue after task `cur_id`: the trainable state (every `prompts.{t}.*` factor and
+        the per-task text contexts -- a few hundred KB; CLIP itself is frozen and reloaded from its own state_dict), the K-Means
+        task keys (sprompt.py:396-397) and the results so far.  The reference's BaseLearner.save_checkpoint (base.py:57-63) is
+        never called and would pickle all 149.8 M parameters."""
+        sd = self._network.state_dict()
+        keep = {k: v.detach().cpu().clone() for k, v in sd.items()
+                if k.startswith("prompts.") or (k.startswith("classifier_pool.") and ".clip_model." not in k)}
+        return {"format": "lpi_b200.checkpoint.v1", "cur_id": int(self.cur_id), "numtask": int(self._network.numtask),
+                "known_classes": int(self._known_classes), "total_classes": int(self._total_classes), "trainable": keep,
+                "all_keys": [k.detach().cpu() for k in self.all_keys],
+                "textual_all_keys": [k.detach().cpu() for k in self.textual_all_keys],
+                "results": {int(t): r for t, r in (results or {}).items()}}
+
+    def save_checkpoint(self, path: str, results: Optional[dict] = None) -> str:
+        tmp = path + ".tmp"
+        torch.save(self.checkpoint_state(results), tmp)
+        os.replace(tmp, path)                              # a crash mid-write never leaves a truncated checkpoint behind
+        return path
+
+    def load_checkpoint(self, path: str) -> dict:
+        """Restores prompts / contexts, task keys and counters; returns the results recorded so far ({task: result dict})."""
+        st = torch.load(path, map_location="cpu", weights_only=False)
+        if st.get("format") != "lpi_b200.checkpoint.v1":
+            raise LpiError(f"{path} is not an lpi_b200 checkpoint")
+        own = self._network.state_dict()
+        missing = [k for k in st["trainable"] if k not in own]
+        if missing:
+            raise LpiError(f"checkpoint keys not in this model: {missing[:3]}...")
+        with torch.no_grad():
+            for k, v in st["trainable"].items():
+                own[k].copy_(v.to(own[k].device, own[k].dtype))
+        self._network.numtask = st["numtask"]
+        self.cur_id = st["cur_id"]
+        self._cur_task = [self.cur_id]
+        self._known_classes, self._total_classes = st["known_classes"], st["total_classes"]
+        self.all_keys = [k.to(self._device) for k in st["all_keys"]]
+        self.textual_all_keys = [k.to(self._device) for k in st["textual_all_keys"]]
+        return {int(t): r for t, r in st["results"].items()}
 
     def save_dict(self, dictionary, file_path):
         with open(file_path, "w") as f:
