@@ -170,7 +170,8 @@ __device__ __forceinline__ float2 unpack_h2(uint32_t w) {
 }
 
 template <int EPI, bool F16 = false>
-__device__ __forceinline__ void epilogue_block(const GemmArgs& p, const float4* __restrict__ st, int row0, int col0, int lane) {
+__device__ __forceinline__ void epilogue_block(const GemmArgs& p, const float4* __restrict__ st, int row0, int col0, int lane,
+                                               const uint2* pre_aux = nullptr) {
     constexpr bool kBias = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_F32 ||
                             EPI == EPI_BIAS_GELU_F32);
     constexpr bool kF32Out = (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_F32 || EPI == EPI_ACC_F32 || EPI == EPI_BIAS_F32 ||
@@ -221,8 +222,10 @@ __device__ __forceinline__ void epilogue_block(const GemmArgs& p, const float4* 
         if (EPI == EPI_DGELU_BF16) {
             uint2 e[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-                e[i] = (i * 4 + rsub < rows) ? *reinterpret_cast<const uint2*>(p.aux_bf16 + base + size_t(i * 4) * p.ldo) : make_uint2(0u, 0u);
+            for (int i = 0; i < 8; ++i) {
+                if (pre_aux) e[i] = pre_aux[i];              // prefetched by the caller while the main loop was still running
+                else e[i] = (i * 4 + rsub < rows) ? *reinterpret_cast<const uint2*>(p.aux_bf16 + base + size_t(i * 4) * p.ldo) : make_uint2(0u, 0u);
+            }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const float2 z0 = unpack_h2<F16>(e[i].x);
@@ -248,6 +251,19 @@ __device__ __forceinline__ void epilogue_block(const GemmArgs& p, const float4* 
             *reinterpret_cast<uint2*>(p.out_bf16 + off) = make_uint2(pack_h2<F16>(v[i].x, v[i].y), pack_h2<F16>(v[i].z, v[i].w));
         }
     }
+}
+
+// The saved pre-activation read by the dGELU epilogue was written a whole forward pass earlier, i.e. it comes from DRAM: loaded
+// inside epilogue_block each 32-column block paid ~1.5 k cycles of exposed latency (4 blocks per tile > the 6 k-cycle main loop of a
+// K = 768 tile).  The pair kernel therefore issues these loads two blocks ahead -- the first two before it even waits for the
+// accumulator -- into registers that are indexed with compile-time constants only.
+__device__ __forceinline__ void prefetch_aux_block(const GemmArgs& p, int row0, int col0, int lane, uint2 (&e)[8]) {
+    const int rows = min(32, p.M - row0);
+    const int rsub = lane >> 3, c = lane & 7;
+    const size_t base = size_t(row0 + rsub) * p.ldo + col0 + c * 4;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        e[i] = (i * 4 + rsub < rows) ? __ldg(reinterpret_cast<const uint2*>(p.aux_bf16 + base + size_t(i * 4) * p.ldo)) : make_uint2(0u, 0u);
 }
 
 // ------------------------------------------------------------------------------------------------ running top-k (MODE_TOPK)
@@ -661,11 +677,17 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tk.cnt = 0;
             for (int nt = n_begin; nt < n_end; ++nt) {
                 const int n0 = nt * BN;
+                constexpr int NCH = BN / 64;                   // 32-column blocks per epilogue warp
+                constexpr bool kPrefetchAux = (MODE == MODE_GEMM) && (EPI == EPI_DGELU_BF16);
+                uint2 pre0[8], pre1[8];
+                if (kPrefetchAux) {
+                    prefetch_aux_block(p, m0 + quad * 32, n0 + (col_half * NCH + 0) * 32, lane, pre0);
+                    prefetch_aux_block(p, m0 + quad * 32, n0 + (col_half * NCH + 1) * 32, lane, pre1);
+                }
                 mbar_wait(tfull_bar(acc), acc_phase);
                 tc_fence_after();
                 if (MODE == MODE_GEMM) {
-#pragma unroll 1
-                    for (int c = col_half * (BN / 64); c < (col_half + 1) * (BN / 64); ++c) {
+                    auto do_block = [&](int c, const uint2* pre) {
                         uint32_t r[32];
                         const uint32_t taddr = tmem_base + uint32_t(acc * BN + c * 32) + (uint32_t(quad * 32) << 16);
                         LPI_TMEM_LD_X32(taddr, r);
@@ -676,8 +698,21 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             stg[lane * 8 + (j ^ (lane & 7))] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
                                                                            __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
                         __syncwarp();
-                        epilogue_block<EPI, F16>(p, stg, m0 + quad * 32, n0 + c * 32, lane);
+                        epilogue_block<EPI, F16>(p, stg, m0 + quad * 32, n0 + c * 32, lane, pre);
                         __syncwarp();
+                    };
+                    if (kPrefetchAux) {
+                        static_assert(NCH == 4, "the aux prefetch schedule below is written for 4 blocks per warp");
+                        const int cb = col_half * NCH;
+                        do_block(cb + 0, pre0);
+                        prefetch_aux_block(p, m0 + quad * 32, n0 + (cb + 2) * 32, lane, pre0);
+                        do_block(cb + 1, pre1);
+                        prefetch_aux_block(p, m0 + quad * 32, n0 + (cb + 3) * 32, lane, pre1);
+                        do_block(cb + 2, pre0);
+                        do_block(cb + 3, pre1);
+                    } else {
+#pragma unroll 1
+                        for (int c = col_half * NCH; c < (col_half + 1) * NCH; ++c) do_block(c, nullptr);
                     }
                 } else {
 #pragma unroll 1
