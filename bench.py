@@ -228,7 +228,7 @@ def run_b200(args):
     # ---------------- e2e: pinned host buffers in, results out, every step
     q_host = q.cpu().pin_memory()
     g_host = shard.cpu().pin_memory()
-    n_parts = max(1, min(8, (hi - lo) // 65536))
+    n_parts = max(1, min(args.e2e_chunks, (hi - lo) // 65536))
     bounds = [R.shard_bounds(hi - lo, n_parts, c, align=256) for c in range(n_parts)]
     g_dev = torch.empty_like(shard)
     q_dev = torch.empty_like(q)
@@ -415,6 +415,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--gallery", type=int, default=5_000_000)
     ap.add_argument("--queries", type=int, default=25_000)
+    ap.add_argument("--e2e-chunks", type=int, default=8, help="host->device pipeline depth of the e2e leg (gallery shard copied in this many pieces)")
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs: no cpu_baseline / parity leg")
     ap.add_argument("--skip-train", action="store_true", help="skip the secondary train pairs/s leg")
     args = ap.parse_args()
