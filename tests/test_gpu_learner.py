@@ -128,3 +128,43 @@ def test_learner_two_tasks_matches_reference(clip_sd, fused, tmp_path, monkeypat
         cat_i = [int(c) for c in ds.cat]
         assert O.itm_eval(s_i2t, s_t2i, ds.txt2img, ds.img2txt, cat_i, ds.text_cat, t + 1) == res
         assert learner.itm_eval(s_i2t, s_t2i, ds.txt2img, ds.img2txt, cat_i, np.asarray(ds.text_cat)) == res
+
+
+def test_incremental_train_checkpoint_and_resume(clip_sd, tmp_path, monkeypatch):
+    """a run resumed from the checkpoint written after task 0 ends in the same state as the uninterrupted run
+    (prompt factors, K-Means task keys, result dicts), and the ./res/*.json it writes feeds the reshandle counterpart."""
+    import glob
+    import json
+
+    from lpi_b200 import reshandle as RH
+
+    monkeypatch.chdir(tmp_path)
+    n_tasks = 3
+
+    def make(**kw):
+        torch.manual_seed(0)
+        args = default_args(clip_state_dict=clip_sd, device=[torch.device("cuda")], epochs=1, batch_size=8, n_tasks=n_tasks, **kw)
+        learner = SPrompts(args)
+        with torch.no_grad():
+            for t in range(n_tasks):
+                for k, v in S.make_prompt_factors(t).items():
+                    getattr(learner._network.prompts[t], k).copy_(v)
+        return learner
+
+    loaders = D.make_task_loaders(n_tasks, 16, 6, 2, 8, 8)
+    a = make(checkpoint_dir=str(tmp_path / "ckpt"))
+    res_a = a.incremental_train(loaders)
+    assert sorted(os.listdir(tmp_path / "ckpt")) == ["task_0.pt", "task_1.pt", "task_2.pt"]
+    assert os.path.getsize(tmp_path / "ckpt" / "task_2.pt") < 2_000_000                  # trainable state only, not the 600 MB CLIP
+    b = make(resume_from=str(tmp_path / "ckpt" / "task_0.pt"))
+    res_b = b.incremental_train(loaders)
+    assert res_b == res_a and set(res_a) == {0, 1, 2}
+    for t in range(n_tasks):
+        for k in O.FACTOR_NAMES:
+            assert torch.allclose(getattr(a._network.prompts[t], k), getattr(b._network.prompts[t], k), rtol=0, atol=1e-6), (t, k)
+        assert torch.equal(a.all_keys[t].cpu(), b.all_keys[t].cpu()) and torch.equal(a.textual_all_keys[t].cpu(), b.textual_all_keys[t].cpu())
+    files = sorted(glob.glob(str(tmp_path / "res" / "*.json")))
+    assert len(files) == 2
+    summary = RH.summarize(json.load(open(files[-1])), "mscoco", "i2t")
+    assert set(summary["per_task"]) == {0, 1, 2} and summary["per_task"][0]["sessions"] == 3
+    assert summary["final"][2] == res_a[2]["mscoco"]["i2t"][2]
