@@ -232,21 +232,27 @@ def run_b200(args):
     bounds = [R.shard_bounds(hi - lo, n_parts, c, align=256) for c in range(n_parts)]
     g_dev = torch.empty_like(shard)
     q_dev = torch.empty_like(q)
-    copy_stream = torch.cuda.Stream()
+    copy_streams = [torch.cuda.Stream() for _ in range(max(1, args.e2e_streams))]
     out_ix = torch.empty(nq, TOPK, dtype=torch.int32).pin_memory()
     out_counts = torch.empty(1, 4, dtype=torch.int32).pin_memory()
 
     def e2e_step():
         main = torch.cuda.current_stream()
-        copy_stream.wait_stream(main)
         evs = []
-        with torch.cuda.stream(copy_stream):
+        for cs in copy_streams:
+            cs.wait_stream(main)
+        with torch.cuda.stream(copy_streams[0]):
             q_dev.copy_(q_host, non_blocking=True)
-            for (a, b) in bounds:
+            q_ev = torch.cuda.Event()
+            q_ev.record(copy_streams[0])
+        for c, (a, b) in enumerate(bounds):                      # chunk c rides copy stream c mod n: several DMA queues keep the link busy
+            cs = copy_streams[c % len(copy_streams)]
+            with torch.cuda.stream(cs):
                 g_dev[a:b].copy_(g_host[a:b], non_blocking=True)
                 ev = torch.cuda.Event()
-                ev.record(copy_stream)
+                ev.record(cs)
                 evs.append(ev)
+        main.wait_event(q_ev)
         lists_s, lists_i = [], []
         for (a, b), ev in zip(bounds, evs):
             main.wait_event(ev)
@@ -337,7 +343,7 @@ def run_b200(args):
                 "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": workload_config(args, world),
                 "e2e": {"value": nq / (e2e_ms * 1e-3), "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": e2e_ms, "steps": e2e_steps},
+                        "ms_per_step": e2e_ms, "steps": e2e_steps, "chunks": n_parts, "copy_streams": len(copy_streams)},
                 "gpu_launches": launches,
                 "clocks": clocks,
                 "roofline": {"bound": "tensor", "kernel": "gemm_pair_kernel<MODE_TOPK> (cta_group::2, resident query tile)", "achieved": ach, "peak": peaks["tflops"],
@@ -416,6 +422,7 @@ def main():
     ap.add_argument("--gallery", type=int, default=5_000_000)
     ap.add_argument("--queries", type=int, default=25_000)
     ap.add_argument("--e2e-chunks", type=int, default=8, help="host->device pipeline depth of the e2e leg (gallery shard copied in this many pieces)")
+    ap.add_argument("--e2e-streams", type=int, default=1, help="copy streams the e2e leg spreads its host->device chunks over")
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs: no cpu_baseline / parity leg")
     ap.add_argument("--skip-train", action="store_true", help="skip the secondary train pairs/s leg")
     args = ap.parse_args()
