@@ -72,10 +72,15 @@ int lpi_gemm_f16(const void* A, const void* B, int M, int N, int K, int epi, con
  * (score desc, global gallery index asc); missing entries are (-inf, INT_MAX).
  * The fp32 accumulation order of a (query, item) score is fixed (K ascending in 16-wide steps), so a score
  * does not depend on tile position, chunking or sharding.
+ * init_thr (optional, element stride init_thr_stride): per-query score s such that only items scoring >= s are kept.  Seeding it
+ * with the k-th best score over ANY subset of the same gallery (e.g. the k-th column of a previous call on its first rows) is exact
+ * -- at least k items reach it, so the true top-k all pass -- and removes most of the list warm-up (sorted insertions), which is a
+ * fixed cost per launch and therefore what limits strong scaling over small shards.
  * ------------------------------------------------------------------------------------------------ */
 int lpi_sim_topk_chunks(int n_queries, int n_gallery, int* n_chunks_out);
 int lpi_sim_topk_bf16(const void* Q, const void* G, int n_queries, int n_gallery, int dim, int k,
-                      long long gallery_offset, int n_chunks, float* part_scores, int* part_idx, void* stream);
+                      long long gallery_offset, int n_chunks, const float* init_thr, int init_thr_stride,
+                      float* part_scores, int* part_idx, void* stream);
 /* k-way merge of n_parts partial lists (chunks and/or all-gathered shards) -> [n_queries, k]. */
 int lpi_topk_merge(const float* part_scores, const int* part_idx, int n_parts, int n_queries, int k,
                    float* out_scores, int* out_idx, void* stream);

@@ -49,6 +49,8 @@ struct GemmArgs {
     int n_chunks;                  // gallery split per query tile (load balance)
     int tiles_per_chunk;
     long long gallery_offset;      // global index of gallery row 0 of this shard
+    int init_thr_stride;           // element stride of init_thr (lets the k-th column of a [M, k] list be used in place)
+    const float* init_thr;         // [M] or null: per-query score every kept candidate must reach (seeded by a pre-pass over a gallery sample)
     float* topk_scores;            // [n_chunks, M, k]
     int* topk_idx;                 // [n_chunks, M, k]
 };
@@ -282,7 +284,7 @@ struct TopkState {
 };
 struct TopkCT { int cnt; float thr; };      // returned by value so both stay in registers across the out-of-line call
 
-__device__ __noinline__ TopkCT topk_insert(float* sc, int* id, int row, int k, int cnt, float v, int gidx) {
+__device__ __noinline__ TopkCT topk_insert(float* sc, int* id, int row, int k, int cnt, float thr_in, float v, int gidx) {
     int pos = cnt < k ? cnt : k - 1;
     while (pos > 0 && sc[(pos - 1) * BM + row] < v) {            // strict: an equal score with a larger index never displaces
         sc[pos * BM + row] = sc[(pos - 1) * BM + row];
@@ -292,30 +294,56 @@ __device__ __noinline__ TopkCT topk_insert(float* sc, int* id, int row, int k, i
     sc[pos * BM + row] = v;
     id[pos * BM + row] = gidx;
     if (cnt < k) ++cnt;
-    return {cnt, cnt == k ? sc[(k - 1) * BM + row] : -INFINITY};
+    return {cnt, cnt == k ? sc[(k - 1) * BM + row] : thr_in};    // a seeded threshold stays in force until the list is full
 }
 
+// largest float below x (x finite or -inf): "v > float_prev(s)" == "v >= s", so a seed taken from k sampled gallery rows admits them again
+__device__ __forceinline__ float float_prev(float x) {
+    if (!(x > -INFINITY)) return -INFINITY;
+    const uint32_t b = __float_as_uint(x);
+    if (x > 0.f) return __uint_as_float(b - 1);
+    if (x == 0.f) return __uint_as_float(0x80000001u);
+    return __uint_as_float(b + 1);
+}
+
+// The check is hierarchical: one compare on the block maximum (hot path), then one per 16-column group, then per element.  During the
+// warm-up of a list some row of the warp passes in most blocks, and the whole warp pays for the slow path, so its cost matters:
+// at 8 GPUs (625 k rows per rank) the flat 64-element scan cost 3.4 ms of a 15.5 ms launch (profiles/r1_scorer_seed.md).
 template <int NCOL>
 __device__ __forceinline__ void topk_consume(TopkState& st, uint32_t (&r)[NCOL], int col0, int n_valid, int gidx0) {
+    static_assert(NCOL % 16 == 0, "group scan");
     if (col0 + NCOL > n_valid) {                  // ragged gallery tail: rows past N were zero-filled by TMA
 #pragma unroll
         for (int j = 0; j < NCOL; ++j)
             if (col0 + j >= n_valid) r[j] = 0xff800000u;   // -inf
     }
-    float m0 = __uint_as_float(r[0]), m1 = __uint_as_float(r[1]);
+    float gmax[NCOL / 16];
 #pragma unroll
-    for (int j = 2; j < NCOL; j += 2) {           // two independent max chains
-        m0 = fmaxf(m0, __uint_as_float(r[j]));
-        m1 = fmaxf(m1, __uint_as_float(r[j + 1]));
+    for (int g = 0; g < NCOL / 16; ++g) {         // independent max chains, one per group
+        float m0 = __uint_as_float(r[16 * g]), m1 = __uint_as_float(r[16 * g + 1]);
+#pragma unroll
+        for (int j = 2; j < 16; j += 2) {
+            m0 = fmaxf(m0, __uint_as_float(r[16 * g + j]));
+            m1 = fmaxf(m1, __uint_as_float(r[16 * g + j + 1]));
+        }
+        gmax[g] = fmaxf(m0, m1);
     }
-    if (fmaxf(m0, m1) > st.thr) {
+    float bmax = gmax[0];
 #pragma unroll
-        for (int j = 0; j < NCOL; ++j) {
-            const float v = __uint_as_float(r[j]);
-            if (v > st.thr) {
-                const TopkCT ct = topk_insert(st.sc, st.id, st.row, st.k, st.cnt, v, gidx0 + col0 + j);
-                st.cnt = ct.cnt;
-                st.thr = ct.thr;
+    for (int g = 1; g < NCOL / 16; ++g) bmax = fmaxf(bmax, gmax[g]);
+    if (bmax > st.thr) {
+#pragma unroll
+        for (int g = 0; g < NCOL / 16; ++g) {
+            if (gmax[g] > st.thr) {
+#pragma unroll
+                for (int j = 16 * g; j < 16 * g + 16; ++j) {
+                    const float v = __uint_as_float(r[j]);
+                    if (v > st.thr) {
+                        const TopkCT ct = topk_insert(st.sc, st.id, st.row, st.k, st.cnt, st.thr, v, gidx0 + col0 + j);
+                        st.cnt = ct.cnt;
+                        st.thr = ct.thr;
+                    }
+                }
             }
         }
     }
@@ -430,7 +458,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
             const int row = m0 + r_local;
-            if (MODE == MODE_TOPK && first) { tk.thr = -INFINITY; tk.cnt = 0; }
+            if (MODE == MODE_TOPK && first) { tk.thr = (p.init_thr && row < p.M) ? float_prev(p.init_thr[size_t(row) * p.init_thr_stride]) : -INFINITY; tk.cnt = 0; }
             if (MODE == MODE_GEMM) {
 #pragma unroll 1
                 for (int c = 0; c < BN / 32; ++c) {
@@ -673,7 +701,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             int n_begin, n_end;
             if (MODE == MODE_GEMM) { n_begin = second; n_end = second + 1; }
             else { n_begin = second * p.tiles_per_chunk; n_end = min(num_n, n_begin + p.tiles_per_chunk); }
-            tk.thr = -INFINITY;
+            tk.thr = (MODE == MODE_TOPK && p.init_thr && row < p.M) ? float_prev(p.init_thr[size_t(row) * p.init_thr_stride]) : -INFINITY;
             tk.cnt = 0;
             for (int nt = n_begin; nt < n_end; ++nt) {
                 const int n0 = nt * BN;
@@ -1003,7 +1031,8 @@ extern "C" int lpi_sim_topk_chunks(int n_queries, int n_gallery, int* n_chunks_o
 }
 
 extern "C" int lpi_sim_topk_bf16(const void* Q, const void* G, int n_queries, int n_gallery, int dim, int k,
-                                 long long gallery_offset, int n_chunks, float* part_scores, int* part_idx, void* stream) {
+                                 long long gallery_offset, int n_chunks, const float* init_thr, int init_thr_stride, float* part_scores,
+                                 int* part_idx, void* stream) {
     if (n_queries <= 0 || n_gallery <= 0) return set_error(LPI_ERR_ARG, "sim_topk: empty problem");
     if (dim % BK) return set_error(LPI_ERR_ARG, "sim_topk: dim=%d must be a multiple of %d", dim, BK);
     if (k < 1 || k > TOPK_MAX) return set_error(LPI_ERR_ARG, "sim_topk: k=%d out of range [1,%d]", k, TOPK_MAX);
@@ -1022,6 +1051,8 @@ extern "C" int lpi_sim_topk_bf16(const void* Q, const void* G, int n_queries, in
     if (long(a.tiles_per_chunk) * (n_chunks - 1) >= nt)
         return set_error(LPI_ERR_ARG, "sim_topk: n_chunks=%d leaves an empty chunk for %d tiles", n_chunks, nt);
     a.gallery_offset = gallery_offset;
+    a.init_thr = init_thr;
+    a.init_thr_stride = init_thr_stride > 0 ? init_thr_stride : 1;
     a.topk_scores = part_scores;
     a.topk_idx = part_idx;
     const int sms = num_sms();

@@ -88,10 +88,18 @@ def sim_topk_chunks(n_queries: int, n_gallery: int) -> int:
     return n.value
 
 
+import os as _os
+
+SEED_ROWS = int(_os.environ.get("LPI_SEED_ROWS", "16384"))   # gallery rows scored first to seed the per-query thresholds of the main pass
+SEED_MIN_GALLERY = 131072    # below this the warm-up is not worth a second launch
+
+
 def sim_topk(q: torch.Tensor, g: torch.Tensor, k: int = 10, gallery_offset: int = 0, n_chunks: int = 0,
-             merge: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+             merge: bool = True, seed_rows: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """Top-k gallery rows per query by dot product; q [nq,dim], g [ng,dim] bf16.
-    Returns (scores fp32, global idx int32), [nq,k] when merged else [n_chunks,nq,k]."""
+    Returns (scores fp32, global idx int32), [nq,k] when merged else [n_chunks,nq,k].
+    seed_rows: None = automatic (a pre-pass over the first SEED_ROWS rows of large galleries supplies per-query thresholds, which
+    leaves the result unchanged and removes most sorted insertions), 0 = off, n = pre-pass over the first n rows."""
     _lib.require_device()
     _chk(q, torch.bfloat16, "q")
     _chk(g, torch.bfloat16, "g")
@@ -99,9 +107,20 @@ def sim_topk(q: torch.Tensor, g: torch.Tensor, k: int = 10, gallery_offset: int 
     ng = g.shape[0]
     if n_chunks <= 0:
         n_chunks = sim_topk_chunks(nq, ng)
+    if seed_rows is None:
+        seed_rows = SEED_ROWS if ng >= SEED_MIN_GALLERY else 0
+    seed_rows = min(int(seed_rows), ng)
+    thr_ptr, thr_stride, seed_scores = None, 1, None
+    if seed_rows >= k:                                         # the k-th column of the sample's list is the seed (-inf if short)
+        seed_scores = torch.empty(1, nq, k, device=q.device, dtype=torch.float32)
+        seed_idx = torch.empty(1, nq, k, device=q.device, dtype=torch.int32)
+        call("sim_topk_bf16", ptr(q), ptr(g), nq, seed_rows, dim, k, C.c_longlong(gallery_offset), 1, None, 1, ptr(seed_scores), ptr(seed_idx),
+             stream_ptr())
+        _count()
+        thr_ptr, thr_stride = C.c_void_p(seed_scores.data_ptr() + 4 * (k - 1)), k
     ps = torch.empty(n_chunks, nq, k, device=q.device, dtype=torch.float32)
     pi = torch.empty(n_chunks, nq, k, device=q.device, dtype=torch.int32)
-    call("sim_topk_bf16", ptr(q), ptr(g), nq, ng, dim, k, C.c_longlong(gallery_offset), n_chunks, ptr(ps), ptr(pi),
+    call("sim_topk_bf16", ptr(q), ptr(g), nq, ng, dim, k, C.c_longlong(gallery_offset), n_chunks, thr_ptr, thr_stride, ptr(ps), ptr(pi),
          stream_ptr())
     _count()
     if not merge:

@@ -55,6 +55,30 @@ def test_gallery_offset_and_shard_merge_equals_unsharded():
         assert torch.equal(i, i0) and torch.equal(v, v0)        # score of a pair does not depend on the sharding
 
 
+@pytest.mark.parametrize("order", ["random", "ascending", "descending"])
+def test_threshold_seeding_is_exact(order):
+    """The seeded two-pass form (thresholds from a pre-pass over the first rows) must return exactly the unseeded lists, including
+    exact ties at the threshold and galleries ordered adversarially (best rows last: the seed helps nothing; best rows first: the
+    seed equals the final k-th score, so every later candidate sits AT the threshold)."""
+    gen = torch.Generator().manual_seed(17)
+    q = torch.randn(300, 512, generator=gen).bfloat16().cuda()
+    g = torch.randn(40000, 512, generator=gen).bfloat16()
+    g[1000:1040] = g[40:80]                       # duplicates of rows inside the seed sample: ties exactly at / above the seed
+    g[39000] = g[7]
+    if order != "random":
+        key = (q[0].float().cpu() @ g.float().t())
+        g = g[torch.argsort(key, descending=(order == "descending"))]
+    g = g.cuda().contiguous()
+    v0, i0 = ops.sim_topk(q, g, 10, 5, seed_rows=0)
+    for seed_rows, chunks in ((512, 0), (4096, 3), (10, 1), (40000, 0)):
+        v, i = ops.sim_topk(q, g, 10, 5, chunks, seed_rows=seed_rows)
+        assert torch.equal(i, i0) and torch.equal(v, v0), (order, seed_rows, chunks)
+    # k larger than the seed sample: the seed list is short, its k-th entry is -inf, nothing is filtered
+    v, i = ops.sim_topk(q, g, 16, 5, seed_rows=12)
+    v1, i1 = ops.sim_topk(q, g, 16, 5, seed_rows=0)
+    assert torch.equal(i, i1) and torch.equal(v, v1)
+
+
 def test_topk_rows_and_merge_ties():
     gen = torch.Generator().manual_seed(11)
     s = torch.randn(70, 4001, generator=gen)
