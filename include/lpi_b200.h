@@ -81,6 +81,11 @@ int lpi_sim_topk_chunks(int n_queries, int n_gallery, int* n_chunks_out);
 int lpi_sim_topk_bf16(const void* Q, const void* G, int n_queries, int n_gallery, int dim, int k,
                       long long gallery_offset, int n_chunks, const float* init_thr, int init_thr_stride,
                       float* part_scores, int* part_idx, void* stream);
+/* Threshold pre-pass for lpi_sim_topk_bf16: seed_scores [n_queries, k] = the k largest per-tile (256 rows) maxima over the first
+ * n_rows gallery rows (seed_idx_ws [n_queries, k] is scratch).  `seed_scores + (k - 1)` with init_thr_stride = k is then a valid
+ * init_thr: k distinct rows reach it.  One candidate per tile keeps the pass MMA-bound. */
+int lpi_sim_topk_seed_bf16(const void* Q, const void* G, int n_queries, int n_rows, int dim, int k, float* seed_scores,
+                           int* seed_idx_ws, void* stream);
 /* k-way merge of n_parts partial lists (chunks and/or all-gathered shards) -> [n_queries, k]. */
 int lpi_topk_merge(const float* part_scores, const int* part_idx, int n_parts, int n_queries, int k,
                    float* out_scores, int* out_idx, void* stream);

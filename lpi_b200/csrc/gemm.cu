@@ -49,6 +49,7 @@ struct GemmArgs {
     int n_chunks;                  // gallery split per query tile (load balance)
     int tiles_per_chunk;
     long long gallery_offset;      // global index of gallery row 0 of this shard
+    int seed_mode;                 // 1: keep the top-k of the per-TILE maxima only (threshold pre-pass: one candidate per 256 gallery rows)
     int init_thr_stride;           // element stride of init_thr (lets the k-th column of a [M, k] list be used in place)
     const float* init_thr;         // [M] or null: per-query score every kept candidate must reach (seeded by a pre-pass over a gallery sample)
     float* topk_scores;            // [n_chunks, M, k]
@@ -306,6 +307,25 @@ __device__ __forceinline__ float float_prev(float x) {
     return __uint_as_float(b + 1);
 }
 
+// maximum of one 64-column accumulator block (ragged tail masked) -- the whole epilogue of the threshold pre-pass
+template <int NCOL>
+__device__ __forceinline__ float block_max(uint32_t (&r)[NCOL], int col0, int n_valid) {
+    if (col0 + NCOL > n_valid) {
+#pragma unroll
+        for (int j = 0; j < NCOL; ++j)
+            if (col0 + j >= n_valid) r[j] = 0xff800000u;
+    }
+    float m[4] = {__uint_as_float(r[0]), __uint_as_float(r[1]), __uint_as_float(r[2]), __uint_as_float(r[3])};
+#pragma unroll
+    for (int j = 4; j < NCOL; j += 4) {
+        m[0] = fmaxf(m[0], __uint_as_float(r[j]));
+        m[1] = fmaxf(m[1], __uint_as_float(r[j + 1]));
+        m[2] = fmaxf(m[2], __uint_as_float(r[j + 2]));
+        m[3] = fmaxf(m[3], __uint_as_float(r[j + 3]));
+    }
+    return fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3]));
+}
+
 // The check is hierarchical: one compare on the block maximum (hot path), then one per 16-column group, then per element.  During the
 // warm-up of a list some row of the warp passes in most blocks, and the whole warp pays for the slow path, so its cost matters:
 // at 8 GPUs (625 k rows per rank) the flat 64-element scan cost 3.4 ms of a 15.5 ms launch (profiles/r1_scorer_seed.md).
@@ -476,13 +496,20 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     __syncwarp();
                 }
             } else {
+                float tmax = -INFINITY;
 #pragma unroll 1
                 for (int c = 0; c < BN / 64; ++c) {
                     uint32_t r[64];
                     const uint32_t taddr = tmem_base + uint32_t(acc * BN + c * 64) + (uint32_t(quad * 32) << 16);
                     LPI_TMEM_LD_X64(taddr, r);
                     tmem_ld_wait();
-                    topk_consume<64>(tk, r, n0 + c * 64, p.N, int(p.gallery_offset));
+                    if (p.seed_mode) tmax = fmaxf(tmax, block_max<64>(r, n0 + c * 64, p.N));
+                    else topk_consume<64>(tk, r, n0 + c * 64, p.N, int(p.gallery_offset));
+                }
+                if (p.seed_mode && tmax > tk.thr) {          // one candidate per tile: its maximum
+                    const TopkCT ct = topk_insert(tk.sc, tk.id, tk.row, tk.k, tk.cnt, tk.thr, tmax, n0);
+                    tk.cnt = ct.cnt;
+                    tk.thr = ct.thr;
                 }
             }
             tc_fence_before();
@@ -743,13 +770,20 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         for (int c = col_half * NCH; c < (col_half + 1) * NCH; ++c) do_block(c, nullptr);
                     }
                 } else {
+                    float tmax = -INFINITY;
 #pragma unroll 1
                     for (int c = 0; c < BN / 64; ++c) {
                         uint32_t r[64];
                         const uint32_t taddr = tmem_base + uint32_t(acc * BN + c * 64) + (uint32_t(quad * 32) << 16);
                         LPI_TMEM_LD_X64(taddr, r);
                         tmem_ld_wait();
-                        topk_consume<64>(tk, r, n0 + c * 64, p.N, int(p.gallery_offset));
+                        if (p.seed_mode) tmax = fmaxf(tmax, block_max<64>(r, n0 + c * 64, p.N));
+                        else topk_consume<64>(tk, r, n0 + c * 64, p.N, int(p.gallery_offset));
+                    }
+                    if (p.seed_mode && tmax > tk.thr) {      // one candidate per tile: its maximum
+                        const TopkCT ct = topk_insert(tk.sc, tk.id, tk.row, tk.k, tk.cnt, tk.thr, tmax, n0);
+                        tk.cnt = ct.cnt;
+                        tk.thr = ct.thr;
                     }
                 }
                 tc_fence_before();
@@ -1030,9 +1064,8 @@ extern "C" int lpi_sim_topk_chunks(int n_queries, int n_gallery, int* n_chunks_o
     return 0;
 }
 
-extern "C" int lpi_sim_topk_bf16(const void* Q, const void* G, int n_queries, int n_gallery, int dim, int k,
-                                 long long gallery_offset, int n_chunks, const float* init_thr, int init_thr_stride, float* part_scores,
-                                 int* part_idx, void* stream) {
+static int sim_topk_impl(const void* Q, const void* G, int n_queries, int n_gallery, int dim, int k, long long gallery_offset, int n_chunks,
+                         const float* init_thr, int init_thr_stride, int seed_mode, float* part_scores, int* part_idx, void* stream) {
     if (n_queries <= 0 || n_gallery <= 0) return set_error(LPI_ERR_ARG, "sim_topk: empty problem");
     if (dim % BK) return set_error(LPI_ERR_ARG, "sim_topk: dim=%d must be a multiple of %d", dim, BK);
     if (k < 1 || k > TOPK_MAX) return set_error(LPI_ERR_ARG, "sim_topk: k=%d out of range [1,%d]", k, TOPK_MAX);
@@ -1051,6 +1084,7 @@ extern "C" int lpi_sim_topk_bf16(const void* Q, const void* G, int n_queries, in
     if (long(a.tiles_per_chunk) * (n_chunks - 1) >= nt)
         return set_error(LPI_ERR_ARG, "sim_topk: n_chunks=%d leaves an empty chunk for %d tiles", n_chunks, nt);
     a.gallery_offset = gallery_offset;
+    a.seed_mode = seed_mode;
     a.init_thr = init_thr;
     a.init_thr_stride = init_thr_stride > 0 ? init_thr_stride : 1;
     a.topk_scores = part_scores;
@@ -1064,4 +1098,19 @@ extern "C" int lpi_sim_topk_bf16(const void* Q, const void* G, int n_queries, in
     const long items = long((n_queries + BM - 1) / BM) * n_chunks;
     const int grid = int(items < sms ? items : sms);
     return launch<MODE_TOPK, 256, EPI_F32>(tmA, tmB, a, grid, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int lpi_sim_topk_bf16(const void* Q, const void* G, int n_queries, int n_gallery, int dim, int k,
+                                 long long gallery_offset, int n_chunks, const float* init_thr, int init_thr_stride, float* part_scores,
+                                 int* part_idx, void* stream) {
+    return sim_topk_impl(Q, G, n_queries, n_gallery, dim, k, gallery_offset, n_chunks, init_thr, init_thr_stride, 0, part_scores, part_idx,
+                         stream);
+}
+
+// Threshold pre-pass: seed_scores[q, 0..k) = the k largest per-tile (256 gallery rows) maxima of query q over the first n_rows rows.
+// The k-th of them is reached by k distinct gallery rows, so `seed_scores + (k - 1)` with stride k is a valid init_thr for
+// lpi_sim_topk_bf16 over any gallery containing these rows; one candidate per tile keeps this pass MMA-bound (no warm-up insertions).
+extern "C" int lpi_sim_topk_seed_bf16(const void* Q, const void* G, int n_queries, int n_rows, int dim, int k, float* seed_scores,
+                                      int* seed_idx_ws, void* stream) {
+    return sim_topk_impl(Q, G, n_queries, n_rows, dim, k, 0, 1, nullptr, 1, 1, seed_scores, seed_idx_ws, stream);
 }

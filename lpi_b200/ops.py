@@ -111,11 +111,10 @@ def sim_topk(q: torch.Tensor, g: torch.Tensor, k: int = 10, gallery_offset: int 
         seed_rows = SEED_ROWS if ng >= SEED_MIN_GALLERY else 0
     seed_rows = min(int(seed_rows), ng)
     thr_ptr, thr_stride, seed_scores = None, 1, None
-    if seed_rows >= k:                                         # the k-th column of the sample's list is the seed (-inf if short)
+    if seed_rows >= k:     # k-th largest per-tile maximum of the sample = the seed (-inf if the sample has fewer than k tiles)
         seed_scores = torch.empty(1, nq, k, device=q.device, dtype=torch.float32)
         seed_idx = torch.empty(1, nq, k, device=q.device, dtype=torch.int32)
-        call("sim_topk_bf16", ptr(q), ptr(g), nq, seed_rows, dim, k, C.c_longlong(gallery_offset), 1, None, 1, ptr(seed_scores), ptr(seed_idx),
-             stream_ptr())
+        call("sim_topk_seed_bf16", ptr(q), ptr(g), nq, seed_rows, dim, k, ptr(seed_scores), ptr(seed_idx), stream_ptr())
         _count()
         thr_ptr, thr_stride = C.c_void_p(seed_scores.data_ptr() + 4 * (k - 1)), k
     ps = torch.empty(n_chunks, nq, k, device=q.device, dtype=torch.float32)
