@@ -109,23 +109,24 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const float* 
     const long row = (long(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     if (row >= M) return;
     const int lane = threadIdx.x & 31;
-    float4 xv[NV], dyv[NV], dx[NV];
+    float4 xv[NV], dyv[NV], dx[NV], gv[NV];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
+    for (int i = 0; i < NV; ++i) {                   // every load of the row is issued before the first reduction: ONE exposed memory latency
         const long o = row * D + (i * 32 + lane) * 4;
         xv[i] = *reinterpret_cast<const float4*>(x + o);
         dyv[i] = *reinterpret_cast<const float4*>(dy + o);
-        if (F16) { dyv[i].x *= dy_scale; dyv[i].y *= dy_scale; dyv[i].z *= dy_scale; dyv[i].w *= dy_scale; }
+        gv[i] = accumulate ? *reinterpret_cast<const float4*>(g + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (F16) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) { dyv[i].x *= dy_scale; dyv[i].y *= dy_scale; dyv[i].z *= dy_scale; dyv[i].w *= dy_scale; }
     }
     ln_bwd_row<NV>(xv, dyv, gamma, D, eps, lane, dx);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
         const long o = row * D + (i * 32 + lane) * 4;
         float4 r = dx[i];
-        if (accumulate) {
-            const float4 p = *reinterpret_cast<const float4*>(g + o);
-            r.x += p.x; r.y += p.y; r.z += p.z; r.w += p.w;
-        }
+        r.x += gv[i].x; r.y += gv[i].y; r.z += gv[i].z; r.w += gv[i].w;
         *reinterpret_cast<float4*>(g + o) = r;
         if (g_bf16) {
             if (F16) { r.x *= shadow_scale; r.y *= shadow_scale; r.z *= shadow_scale; r.w *= shadow_scale; }

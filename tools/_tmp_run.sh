@@ -1,0 +1,4 @@
+export PATH=/usr/local/cuda/bin:$PATH
+timeout 900 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_model.py -m gpu -q --tb=short 2>&1 | tail -3
+python tools/bench_train.py --batch 64
+python tools/bench_train.py --batch 64
