@@ -141,6 +141,10 @@ int lpi_layernorm_fwd_f16(const float* x, const float* gamma, const float* beta,
                           float eps, void* stream);
 int lpi_layernorm_bwd_f16(const float* dy_scaled, const float* x, const float* gamma, float* g, void* g_f16, long long M, int D,
                           float eps, int accumulate, float grad_scale, void* stream);
+/* dy in the tower's 16-bit type, as written by the dgrad GEMM's EPI_BF16 epilogue (bf16: is_f16 = 0, grad_scale ignored; fp16:
+ * is_f16 = 1, dy carries grad_scale): halves the largest stream of this HBM-bound kernel. */
+int lpi_layernorm_bwd_dy16(const void* dy16, int is_f16, const float* x, const float* gamma, float* g, void* g16, long long M, int D,
+                           float eps, int accumulate, float grad_scale, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Vision front end (VisionTransformer.forward, models/clip/model.py:227-250).

@@ -102,7 +102,9 @@ __device__ __forceinline__ void ln_bwd_row(const float4 (&xv)[NV], const float4 
 
 // F16: the fp16 gradient path carries gradients multiplied by `shadow_scale` (a power of two) so small values stay in fp16's
 // normal range: dy arrives scaled (dy_scale = 1 / shadow_scale brings it back), g stays true-scale fp32, the shadow is scaled again.
-template <int NV, bool F16 = false>
+// DY16: dy arrives in the tower's 16-bit type (bf16, or fp16 when F16) straight from the dgrad GEMM's epilogue -- half the bytes of
+// the largest stream this HBM-bound kernel reads.
+template <int NV, bool F16 = false, bool DY16 = false>
 __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
                                      float* __restrict__ g, __nv_bfloat16* __restrict__ g_bf16, long M, int D, float eps, int accumulate,
                                      float dy_scale = 1.0f, float shadow_scale = 1.0f) {
@@ -114,7 +116,14 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const float* 
     for (int i = 0; i < NV; ++i) {                   // every load of the row is issued before the first reduction: ONE exposed memory latency
         const long o = row * D + (i * 32 + lane) * 4;
         xv[i] = *reinterpret_cast<const float4*>(x + o);
-        dyv[i] = *reinterpret_cast<const float4*>(dy + o);
+        if (DY16) {
+            const uint2 w = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(dy) + o);
+            const float2 a = F16 ? __half22float2(*reinterpret_cast<const __half2*>(&w.x)) : __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.x));
+            const float2 b = F16 ? __half22float2(*reinterpret_cast<const __half2*>(&w.y)) : __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w.y));
+            dyv[i] = make_float4(a.x, a.y, b.x, b.y);
+        } else {
+            dyv[i] = *reinterpret_cast<const float4*>(dy + o);
+        }
         gv[i] = accumulate ? *reinterpret_cast<const float4*>(g + o) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     if (F16) {
@@ -454,6 +463,22 @@ extern "C" int lpi_layernorm_bwd_f16(const float* dy_scaled, const float* x, con
         return 0;
     });
     return rc ? rc : check_launch("layernorm_bwd_f16");
+}
+
+extern "C" int lpi_layernorm_bwd_dy16(const void* dy16, int is_f16, const float* x, const float* gamma, float* g, void* g16, long long M, int D,
+                                      float eps, int accumulate, float grad_scale, void* stream) {
+    if (M <= 0) return LPI_OK;
+    if (is_f16 && !(grad_scale > 0.f)) return set_error(LPI_ERR_ARG, "layernorm_bwd_dy16: grad_scale must be positive");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const float* dy = static_cast<const float*>(dy16);       // reinterpreted inside the kernel
+    auto gh = static_cast<__nv_bfloat16*>(g16);
+    const int rc = dispatch_nv(D, [&](auto nv) {
+        constexpr int NV = decltype(nv)::value;
+        if (is_f16) layernorm_bwd_kernel<NV, true, true><<<warp_grid(M, 128), 128, 0, st>>>(dy, x, gamma, g, gh, M, D, eps, accumulate, 1.0f / grad_scale, grad_scale);
+        else layernorm_bwd_kernel<NV, false, true><<<warp_grid(M, 128), 128, 0, st>>>(dy, x, gamma, g, gh, M, D, eps, accumulate);
+        return 0;
+    });
+    return rc ? rc : check_launch("layernorm_bwd_dy16");
 }
 
 extern "C" int lpi_layernorm_bwd(const float* dy, const float* x, const float* gamma, float* g, void* g_bf16, long long M, int D, float eps,

@@ -107,6 +107,10 @@ class Tower:
         # fp16 gradient path: the 16-bit gradient stream is carried times 2^10 so that small gradients stay in fp16's normal range
         # (min normal 6.1e-5); every op between two LayerNorm backwards is linear in the gradient, so the factor is exact.
         self.grad_scale = 1024.0 if precision == "fp16" else None
+        # the dgrad GEMMs feeding the two LayerNorm backwards hand dy over in 16 bits (half the bytes of those HBM-bound kernels' largest
+        # stream); LPI_DH_F32=1 keeps them fp32 for precision studies
+        import os
+        self.epi_dh = ops.EPI_F32 if os.environ.get("LPI_DH_F32") == "1" else ops.EPI_BF16
         self.blocks = load_blocks(sd, prefix, dev, need_grad, self.tf32, self.half)
         self.heads = heads
         self.causal = causal
@@ -193,11 +197,11 @@ class Tower:
         for li in range(len(self.blocks) - 1, -1, -1):
             w, s = self.blocks[li], tape.blocks[li]
             dz = ops.gemm(g_bf16, w.w_proj_t, ops.EPI_DGELU_BF16, aux=s.z)
-            dh2 = ops.gemm(dz, w.w_fc_t, ops.EPI_F32)
+            dh2 = ops.gemm(dz, w.w_fc_t, self.epi_dh)
             ops.layernorm_bwd(dh2, s.x1, w.ln2_g, g, g_bf16, accumulate=True, grad_scale=self.grad_scale)
             do = ops.gemm(g_bf16, w.w_out_t, ops.EPI_BF16)
             dqkv = ops.attn_bwd(s.qkv, s.o, do, s.lse, B, L, H, self.causal)
-            dh1 = ops.gemm(dqkv, w.w_in_t, ops.EPI_F32)
+            dh1 = ops.gemm(dqkv, w.w_in_t, self.epi_dh)
             ops.layernorm_bwd(dh1, s.x, w.ln1_g, g, g_bf16, accumulate=True, grad_scale=self.grad_scale)
             if inject is not None and li != 0 and li in inject["layers"] and inject_grads is not None:
                 n_tables = inject["table"].shape[0]

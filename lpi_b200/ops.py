@@ -260,19 +260,25 @@ def layernorm_fwd(x, gamma, beta, want_f32=False, want_bf16=True, half_dtype=tor
 
 
 def layernorm_bwd(dy, x, gamma, g, g_bf16=None, accumulate=True, grad_scale: Optional[float] = None):
-    """g = (accumulate ? g : 0) + dLN(dy; x, gamma), in place; optional 16-bit shadow.  With grad_scale (fp16 gradient path):
-    dy is grad_scale * (true dy), g stays true scale, the fp16 shadow is grad_scale * g."""
-    for t, n in ((dy, "dy"), (x, "x"), (g, "g")):
+    """g = (accumulate ? g : 0) + dLN(dy; x, gamma), in place; optional 16-bit shadow.  dy may be fp32 or the tower's 16-bit type
+    (bf16 / fp16, as written by a dgrad GEMM).  With grad_scale (fp16 gradient path): dy is grad_scale * (true dy), g stays true
+    scale, the fp16 shadow is grad_scale * g."""
+    for t, n in ((x, "x"), (g, "g")):
         _chk(t, torch.float32, n)
     M, D = x.shape
-    if grad_scale is not None:
-        if g_bf16 is not None:
-            _chk(g_bf16, torch.float16, "g_f16")
+    half = torch.float16 if grad_scale is not None else torch.bfloat16
+    if g_bf16 is not None:
+        _chk(g_bf16, half, "g16")
+    if dy.dtype in (torch.bfloat16, torch.float16):
+        _chk(dy, half, "dy")
+        call("layernorm_bwd_dy16", ptr(dy), int(half == torch.float16), ptr(x), ptr(gamma), ptr(g), ptr(g_bf16), C.c_longlong(M), D,
+             C.c_float(LN_EPS), int(accumulate), C.c_float(grad_scale if grad_scale is not None else 1.0), stream_ptr())
+    elif grad_scale is not None:
+        _chk(dy, torch.float32, "dy")
         call("layernorm_bwd_f16", ptr(dy), ptr(x), ptr(gamma), ptr(g), ptr(g_bf16), C.c_longlong(M), D, C.c_float(LN_EPS), int(accumulate),
              C.c_float(grad_scale), stream_ptr())
     else:
-        if g_bf16 is not None:
-            _chk(g_bf16, torch.bfloat16, "g_bf16")
+        _chk(dy, torch.float32, "dy")
         call("layernorm_bwd", ptr(dy), ptr(x), ptr(gamma), ptr(g), ptr(g_bf16), C.c_longlong(M), D, C.c_float(LN_EPS), int(accumulate),
              stream_ptr())
     _count()
