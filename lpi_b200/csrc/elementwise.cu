@@ -245,15 +245,23 @@ __global__ void assemble_text_kernel(const float* __restrict__ emb, const long l
     }
 }
 
-// d ctx_table[t, p, :] = sum over {b : sel[b] == t} g[b, 1+p, :]        grid = (P, T), thread per column
+// d ctx_table[t, p, :] = sum over {b : sel[b] == t} g[b, 1+p, :]        grid = (P, T, ceil(D / 128)), block = 128 columns x 8 batch slices
 __global__ void assemble_text_bwd_kernel(const float* __restrict__ g, const int* __restrict__ sel, float* __restrict__ d_ctx, int B, int L, int P,
                                          int D) {
+    __shared__ float part[8][128];
     const int p = blockIdx.x, t = blockIdx.y;
-    for (int c = threadIdx.x; c < D; c += blockDim.x) {
-        float s = 0.f;
-        for (int b = 0; b < B; ++b)
+    const int c = blockIdx.z * 128 + threadIdx.x, sl = threadIdx.y;
+    float s = 0.f;
+    if (c < D)
+        for (int b = sl; b < B; b += 8)                  // fixed order per slice, slices combined in order below: deterministic
             if ((sel ? sel[b] : 0) == t) s += g[(long(b) * L + 1 + p) * D + c];
-        d_ctx[(long(t) * P + p) * D + c] = s;
+    part[sl][threadIdx.x] = s;
+    __syncthreads();
+    if (sl == 0 && c < D) {
+        float v = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v += part[j][threadIdx.x];
+        d_ctx[(long(t) * P + p) * D + c] = v;
     }
 }
 
@@ -542,7 +550,7 @@ extern "C" int lpi_assemble_text(const float* token_embedding, const long long* 
 
 extern "C" int lpi_assemble_text_bwd(const float* g, const int* sel, float* d_ctx, int B, int L, int P, int n_tables, int D, void* stream) {
     if (B <= 0 || P <= 0) return LPI_OK;
-    assemble_text_bwd_kernel<<<dim3(P, n_tables), 256, 0, static_cast<cudaStream_t>(stream)>>>(g, sel, d_ctx, B, L, P, D);
+    assemble_text_bwd_kernel<<<dim3(P, n_tables, (D + 127) / 128), dim3(128, 8), 0, static_cast<cudaStream_t>(stream)>>>(g, sel, d_ctx, B, L, P, D);
     return check_launch("assemble_text_bwd");
 }
 
