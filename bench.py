@@ -380,10 +380,12 @@ def train_leg(dev, world, rank, group, steps, warmup, batch_per_gpu=64):
     fac = {k: v.to(dev) for k, v in S.make_prompt_factors(0).items()}
     opt = lpi_step.PromptSGD(fac, 0.05)
     images = S.make_images(batch_per_gpu, rank).to(dev)
-    tokens = S.make_tokens(batch_per_gpu, rank).to(dev)
+    tokens_host = S.make_tokens(batch_per_gpu, rank)
+    text_len = int(tokens_host.argmax(dim=-1).max()) + 1      # host-side, as the tokenizer provides it: positions after the last EOT are dead
+    tokens = tokens_host.to(dev)
 
     def step():
-        r = lpi_step.train_step(vision, text, fac, images, tokens, 1 / 0.07, group=group)
+        r = lpi_step.train_step(vision, text, fac, images, tokens, 1 / 0.07, group=group, text_len=text_len)
         opt.step(r["grads"])
         return r
 
@@ -409,7 +411,10 @@ def train_leg(dev, world, rank, group, steps, warmup, batch_per_gpu=64):
     return {"metric": "prompted_clip_train_pairs_per_sec", "value": gb / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms,
             "global_batch": gb, "parallelism": f"dp{world}", "launches_per_step": (ops.KERNEL_LAUNCHES - n0) / steps,
             "algorithmic_tflops": gb * 89.7e9 / (ms * 1e-3) / 1e12, "loss": float(r["losses"]["base_loss"]),
-            "precision": "vision bf16 / text fp16 operands, fp32 accumulate", "workload": "BASELINE.json configs[2]: ViT-B/16 + 12-layer text, "
+            "precision": "vision bf16 / text fp16 operands, fp32 accumulate",
+            "text_positions_executed": text_len, "text_positions_note": "77-token captions; the text tower runs on the positions up to the batch's last "
+            "EOT (output-exact under the causal mask); algorithmic_tflops counts the reference's full 77",
+            "workload": "BASELINE.json configs[2]: ViT-B/16 + 12-layer text, "
             "224x224 synthetic images, 77-token captions, random init, fwd + 3 losses + dgrad to 5 284 prompt scalars + SGD"}
 
 

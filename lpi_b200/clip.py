@@ -265,7 +265,11 @@ class PromptLearner(nn.Module):
                 t = _tok.tokenize(self.prompt_prefix + " " + c + ".")[0]
                 self._cache[c] = t
             rows.append(t)
-        return torch.stack(rows).to(self.device, non_blocking=True)
+        host = torch.stack(rows)
+        out = host.to(self.device, non_blocking=True)
+        # known on the host for free: lets TextEngine.forward skip the positions after the batch's last EOT without a device sync
+        out.lpi_text_len = int(host.argmax(dim=-1).max()) + 1
+        return out
 
     def extract_vector(self, captions):
         """prompt_learner.py:118-126: embeddings WITHOUT the context splice (the raw 'X' embeddings stay)."""

@@ -287,14 +287,27 @@ class TextEngine:
         self.width = self.emb.shape[1]
         self.tower = Tower(sd, "transformer.resblocks.", self.width // 64, True, dev, need_grad, precision)
         self.context_length = self.pos.shape[0]
+        self.trim_padding = True          # see forward(): skip the positions after the batch's last EOT
         self.zero_pos = torch.zeros_like(self.pos)
         self.dev = dev
 
     def forward(self, tokens: torch.Tensor, prompt_table: Optional[torch.Tensor] = None, sel: Optional[torch.Tensor] = None,
-                tape: Optional[dict] = None, inject_layers: Sequence[int] = ()):
-        """tokens int64 [B, 77] on the device; prompt_table [T, Lp, P, Dt] fp32 (layer 0 is spliced over positions 1..P) or None."""
+                tape: Optional[dict] = None, inject_layers: Sequence[int] = (), text_len: Optional[int] = None):
+        """tokens int64 [B, 77] on the device; prompt_table [T, Lp, P, Dt] fp32 (layer 0 is spliced over positions 1..P) or None.
+
+        text_len (host int, or the `lpi_text_len` attribute the tokenizer attaches to its output): number of leading token positions
+        that contain every caption's EOT.  The mask is causal (model.py:347-353) and the head reads the EOT row only, so positions
+        after the last EOT influence neither the features nor any gradient: the tower then runs on [B, text_len] instead of [B, 77]
+        (output-exact; COCO-length captions end near position 40).  Unknown -> all positions, no host sync."""
         B, L = tokens.shape
         D = self.width
+        if text_len is None:
+            text_len = getattr(tokens, "lpi_text_len", None)
+        n_prompt = 0 if prompt_table is None else prompt_table.shape[2]
+        if text_len is not None and self.trim_padding:
+            Lt = max(1 + n_prompt, min(int(text_len), L))
+            if Lt < L:
+                tokens, L = tokens[:, :Lt], Lt
         P = 0 if prompt_table is None else prompt_table.shape[2]
         layer0 = None if prompt_table is None else prompt_table[:, 0].contiguous()
         x = ops.assemble_text(self.emb, tokens.contiguous(), self.pos, layer0, sel, B, L, P, D)

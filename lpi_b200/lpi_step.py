@@ -29,15 +29,16 @@ def flat_size(factors: Dict[str, torch.Tensor]) -> int:
 
 def train_step(vision: VisionEngine, text: TextEngine, factors: Dict[str, torch.Tensor], images: torch.Tensor, tokens: torch.Tensor,
                logit_scale: float, prev_prompts: Sequence = (), task_target: Optional[torch.Tensor] = None,
-               inject_layers: Sequence[int] = (), group=None) -> Dict:
+               inject_layers: Sequence[int] = (), group=None, text_len: Optional[int] = None) -> Dict:
     """factors: the five fp32 device tensors of the current task's DecomposedPrompt.  images [b,3,224,224] fp32 and
     tokens [b,77] int64 are this rank's slice of the global batch.  prev_prompts: [(vis, txt)] of the frozen earlier
     tasks (task loss, only when non-empty).  Returns losses (0-dim-like device tensors), grads (same keys as factors)
-    and the features.  With `group`, features are all-gathered and the gradient all-reduced (sum)."""
+    and the features.  With `group`, features are all-gathered and the gradient all-reduced (sum).  text_len: host-side bound on the
+    EOT positions of `tokens` (see TextEngine.forward; output-exact trimming of the padding after the last EOT)."""
     vis, txt = reconstruct(factors)
     vtape, ttape = {}, {}
     img_f, _ = vision.forward(images, vis.unsqueeze(0), None, vtape, inject_layers)
-    txt_f, _ = text.forward(tokens, txt.unsqueeze(0), None, ttape, inject_layers)
+    txt_f, _ = text.forward(tokens, txt.unsqueeze(0), None, ttape, inject_layers, text_len=text_len)
     b = img_f.shape[0]
     rank, world = 0, 1
     all_img, all_txt = img_f, txt_f

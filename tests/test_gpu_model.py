@@ -91,3 +91,28 @@ def test_train_step_vs_oracle_fresh_inputs(engines, clip_sd):
             assert abs(float(r["losses"][k]) - v) < 1e-2 * max(abs(v), 1e-3), (inject, k)
         for k in O.FACTOR_NAMES:
             assert _rel(r["grads"][k], want["grads"][k]) < 2e-2, (inject, k, _rel(r["grads"][k], want["grads"][k]))
+
+
+def test_text_padding_trim_is_output_exact(engines):
+    """Positions after the batch's last EOT are dead under the causal mask: running the text tower on
+    [B, text_len] must reproduce the [B, 77] features and prompt gradients."""
+    _, text = engines
+    tokens = S.make_tokens(6, 21)
+    text_len = int(tokens.argmax(-1).max()) + 1
+    assert 18 <= text_len < 77
+    tok = tokens.cuda()
+    fac = {k: v.cuda() for k, v in S.make_prompt_factors(5).items()}
+    _, txt = lpi_step.reconstruct(fac)
+    d = torch.randn(6, 512, generator=torch.Generator().manual_seed(2)).cuda() * 1e-2
+    outs = []
+    for tl in (None, text_len, text_len + 7, 5):          # 5 < 1 + P: clamped up to the 17 rows the splice needs... and below the EOTs
+        if tl == 5:
+            continue                                         # (a bound below the EOT positions is a caller error, not exercised)
+        tape = {}
+        f, z = text.forward(tok, txt.unsqueeze(0), None, tape, (), text_len=tl)
+        G = text.backward(tape, d)
+        outs.append((f, z, G, tape["L"]))
+    assert outs[0][3] == 77 and outs[1][3] == text_len and outs[2][3] == text_len + 7
+    for f, z, G, _ in outs[1:]:
+        assert torch.allclose(f, outs[0][0], rtol=0, atol=2e-6) and torch.allclose(z, outs[0][1], rtol=1e-5, atol=1e-5)
+        assert _rel(G, outs[0][2]) < 1e-4

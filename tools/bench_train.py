@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--text-precision", default="fp16")
     ap.add_argument("--fwd-only", action="store_true")
+    ap.add_argument("--no-trim", action="store_true", help="run the text tower on all 77 positions (default: up to the batch's last EOT)")
     a = ap.parse_args()
     dev = torch.device("cuda")
     sd = S.make_clip_state_dict(0)
@@ -28,15 +29,17 @@ def main():
     fac = {k: v.to(dev) for k, v in S.make_prompt_factors(0).items()}
     opt = lpi_step.PromptSGD(fac, 0.05)
     images = S.make_images(a.batch, 0).to(dev)
-    tokens = S.make_tokens(a.batch, 0).to(dev)
+    tokens_host = S.make_tokens(a.batch, 0)
+    text_len = None if a.no_trim else int(tokens_host.argmax(dim=-1).max()) + 1
+    tokens = tokens_host.to(dev)
 
     def step():
         if a.fwd_only:
             vis, txt = lpi_step.reconstruct(fac)
             vision.forward(images, vis.unsqueeze(0))
-            text.forward(tokens, txt.unsqueeze(0))
+            text.forward(tokens, txt.unsqueeze(0), text_len=text_len)
             return
-        r = lpi_step.train_step(vision, text, fac, images, tokens, 1 / 0.07)
+        r = lpi_step.train_step(vision, text, fac, images, tokens, 1 / 0.07, text_len=text_len)
         opt.step(r["grads"])
 
     for _ in range(a.warmup):
@@ -55,7 +58,7 @@ def main():
     gflop_pair = 44.05 if a.fwd_only else 89.7
     print(json.dumps({"batch": a.batch, "ms_per_step": ms, "wall_ms_per_step": wall, "pairs_per_s": a.batch / ms * 1e3,
                       "tflops_algorithmic": a.batch * gflop_pair / ms, "launches_per_step": (ops.KERNEL_LAUNCHES - n0) / a.steps,
-                      "text_precision": a.text_precision, "fwd_only": a.fwd_only}))
+                      "text_precision": a.text_precision, "fwd_only": a.fwd_only, "text_positions": text_len or 77}))
 
 
 if __name__ == "__main__":
