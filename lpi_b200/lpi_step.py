@@ -9,6 +9,7 @@ The nn.Module / autograd mirror of the same maths lives in slinet.py; both call 
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -17,6 +18,16 @@ from . import losses, ops
 from .engine import TextEngine, VisionEngine
 
 FACTOR_NAMES = ("dim_1_share", "dim_2_visual", "dim_2_textual", "dim_3_visual", "dim_3_textual")
+OVERLAP_TOWERS = os.environ.get("LPI_OVERLAP_TOWERS", "1") != "0"
+_SIDE_STREAMS: Dict = {}
+
+
+def _side_stream(device) -> "torch.cuda.Stream":
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    st = _SIDE_STREAMS.get(key)
+    if st is None:
+        st = _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return st
 
 
 def reconstruct(factors: Dict[str, torch.Tensor]):
@@ -29,16 +40,30 @@ def flat_size(factors: Dict[str, torch.Tensor]) -> int:
 
 def train_step(vision: VisionEngine, text: TextEngine, factors: Dict[str, torch.Tensor], images: torch.Tensor, tokens: torch.Tensor,
                logit_scale: float, prev_prompts: Sequence = (), task_target: Optional[torch.Tensor] = None,
-               inject_layers: Sequence[int] = (), group=None, text_len: Optional[int] = None) -> Dict:
+               inject_layers: Sequence[int] = (), group=None, text_len: Optional[int] = None, overlap_towers: Optional[bool] = None) -> Dict:
     """factors: the five fp32 device tensors of the current task's DecomposedPrompt.  images [b,3,224,224] fp32 and
     tokens [b,77] int64 are this rank's slice of the global batch.  prev_prompts: [(vis, txt)] of the frozen earlier
     tasks (task loss, only when non-empty).  Returns losses (0-dim-like device tensors), grads (same keys as factors)
     and the features.  With `group`, features are all-gathered and the gradient all-reduced (sum).  text_len: host-side bound on the
     EOT positions of `tokens` (see TextEngine.forward; output-exact trimming of the padding after the last EOT)."""
+    if overlap_towers is None:
+        overlap_towers = OVERLAP_TOWERS
     vis, txt = reconstruct(factors)
     vtape, ttape = {}, {}
-    img_f, _ = vision.forward(images, vis.unsqueeze(0), None, vtape, inject_layers)
-    txt_f, _ = text.forward(tokens, txt.unsqueeze(0), None, ttape, inject_layers, text_len=text_len)
+    side = _side_stream(images.device) if overlap_towers else None
+    main = torch.cuda.current_stream()
+    if side is not None:
+        # the text tower's kernels are small (M = b x ~40 rows: 20-40 of the 74 CTA pairs busy, LayerNorm / attention grids far below one
+        # wave), so it runs on a second stream next to the vision tower and fills the SMs that tower's non-persistent kernels leave idle
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            txt_f, _ = text.forward(tokens, txt.unsqueeze(0), None, ttape, inject_layers, text_len=text_len)
+        img_f, _ = vision.forward(images, vis.unsqueeze(0), None, vtape, inject_layers)
+        main.wait_stream(side)
+        txt_f.record_stream(main)
+    else:
+        img_f, _ = vision.forward(images, vis.unsqueeze(0), None, vtape, inject_layers)
+        txt_f, _ = text.forward(tokens, txt.unsqueeze(0), None, ttape, inject_layers, text_len=text_len)
     b = img_f.shape[0]
     rank, world = 0, 1
     all_img, all_txt = img_f, txt_f
@@ -53,8 +78,17 @@ def train_step(vision: VisionEngine, text: TextEngine, factors: Dict[str, torch.
             E = img_f.shape[1]
             all_img, all_txt = gathered[:, :E].contiguous(), gathered[:, E:].contiguous()
     base, d_img, d_txt, logits = losses.contrastive_fwd_bwd(all_img, all_txt, logit_scale, rank * b, b)
-    G_vis = vision.backward(vtape, d_img)[0]          # [Lp, P, Dv]: batch-summed (prompts are `expand`ed, slinet.py:119,129)
-    G_txt = text.backward(ttape, d_txt)[0]
+    if side is not None:
+        side.wait_stream(main)
+        d_txt.record_stream(side)
+        with torch.cuda.stream(side):
+            G_txt = text.backward(ttape, d_txt)[0]
+        G_vis = vision.backward(vtape, d_img)[0]      # [Lp, P, Dv]: batch-summed (prompts are `expand`ed, slinet.py:119,129)
+        main.wait_stream(side)
+        G_txt.record_stream(main)
+    else:
+        G_vis = vision.backward(vtape, d_img)[0]
+        G_txt = text.backward(ttape, d_txt)[0]
     if world > 1:
         # replicated terms (alignment / task losses) are added once after the all-reduce, not world times
         enc = _factor_grads(factors, G_vis, G_txt)
