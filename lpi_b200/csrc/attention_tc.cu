@@ -630,14 +630,7 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
 static int make_tmap_rows3d(CUtensorMap* m, const void* ptr, int B, int L, int cols, int box_rows, bool f16 = false) {
     if (int rc = ensure_tma_encoder()) return rc;
     if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (cols % 8)) return set_error(LPI_ERR_ARG, "attention: operand must be 16-byte aligned");
-    static PFN_encodeTiled enc = nullptr;
-    if (!enc) {
-        void* fn = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn)
-            return set_error(LPI_ERR_CUDA, "cuTensorMapEncodeTiled unavailable");
-        enc = reinterpret_cast<PFN_encodeTiled>(fn);
-    }
+    const PFN_encodeTiled enc = tma_encoder();
     cuuint64_t dims[3] = {cuuint64_t(cols), cuuint64_t(L), cuuint64_t(B)};
     cuuint64_t strides[2] = {cuuint64_t(cols) * 2, cuuint64_t(L) * cols * 2};
     cuuint32_t box[3] = {64, cuuint32_t(box_rows), 1};

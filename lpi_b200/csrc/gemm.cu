@@ -824,6 +824,8 @@ int ensure_tma_encoder() {
     return 0;
 }
 
+PFN_encodeTiled tma_encoder() { return g_encode; }      // valid after ensure_tma_encoder()
+
 // 2D row-major [rows, cols] tensor map with a [box_rows, box_cols] box, SWIZZLE_128B.
 int make_tmap_2d(CUtensorMap* m, const void* ptr, CUtensorMapDataType dt, int elem_bytes, uint64_t rows, uint64_t cols,
                  uint64_t ld_elems, uint32_t box_rows, uint32_t box_cols) {

@@ -16,6 +16,7 @@ int set_error(int code, const char* fmt, ...);   // records lpi_last_error(), re
 int check_launch(const char* what);              // cudaGetLastError -> error code
 int num_sms();
 int ensure_tma_encoder();
+PFN_encodeTiled tma_encoder();                    // cuTensorMapEncodeTiled entry point (after ensure_tma_encoder() returned 0)
 int make_tmap_2d(CUtensorMap* m, const void* ptr, CUtensorMapDataType dt, int elem_bytes, uint64_t rows, uint64_t cols,
                  uint64_t ld_elems, uint32_t box_rows, uint32_t box_cols);
 
