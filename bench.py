@@ -384,10 +384,19 @@ def train_leg(dev, world, rank, group, steps, warmup, batch_per_gpu=64):
     text_len = int(tokens_host.argmax(dim=-1).max()) + 1      # host-side, as the tokenizer provides it: positions after the last EOT are dead
     tokens = tokens_host.to(dev)
 
-    def step():
+    def eager_step():
         r = lpi_step.train_step(vision, text, fac, images, tokens, 1 / 0.07, group=group, text_len=text_len)
         opt.step(r["grads"])
         return r
+
+    step, mode = eager_step, "eager"
+    if os.environ.get("LPI_TRAIN_GRAPH", "1") != "0":
+        try:                                               # one cudaGraphLaunch per step instead of ~400 Python-issued launches
+            graphed = lpi_step.GraphedTrainStep(vision, text, fac, opt, images, tokens, 1 / 0.07, group=group, text_len=text_len)
+            step, mode = graphed.step, "cuda-graph"
+        except Exception as e:                             # capture is an optimisation: fall back to the eager step
+            print(f"[bench] CUDA-graph capture of the training step failed, running eagerly: {e!r}", file=sys.stderr)
+            torch.cuda.synchronize()
 
     for _ in range(warmup):
         step()
@@ -409,7 +418,7 @@ def train_leg(dev, world, rank, group, steps, warmup, batch_per_gpu=64):
     ms = float(ms)
     gb = batch_per_gpu * world
     return {"metric": "prompted_clip_train_pairs_per_sec", "value": gb / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms,
-            "global_batch": gb, "parallelism": f"dp{world}", "launches_per_step": (ops.KERNEL_LAUNCHES - n0) / steps,
+            "global_batch": gb, "parallelism": f"dp{world}", "launch_mode": mode, "launches_per_step": (ops.KERNEL_LAUNCHES - n0) / steps,
             "algorithmic_tflops": gb * 89.7e9 / (ms * 1e-3) / 1e12, "loss": float(r["losses"]["base_loss"]),
             "precision": "vision bf16 / text fp16 operands, fp32 accumulate",
             "text_positions_executed": text_len, "text_positions_note": "77-token captions; the text tower runs on the positions up to the batch's last "

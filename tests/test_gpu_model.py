@@ -116,3 +116,31 @@ def test_text_padding_trim_is_output_exact(engines):
     for f, z, G, _ in outs[1:]:
         assert torch.allclose(f, outs[0][0], rtol=0, atol=2e-6) and torch.allclose(z, outs[0][1], rtol=1e-5, atol=1e-5)
         assert _rel(G, outs[0][2]) < 1e-4
+
+
+def test_graphed_train_step_equals_eager(engines):
+    """CUDA-graph replay (two streams captured) reproduces the eager step: same losses / gradients, and the factors after three SGD
+    steps agree; a new batch copied into the captured buffers changes the result accordingly."""
+    vision, text = engines
+    images, tokens = S.make_images(4, 3).cuda(), S.make_tokens(4, 3)
+    text_len = int(tokens.argmax(-1).max()) + 1
+    tokens = tokens.cuda()
+    fa = {k: v.cuda() for k, v in S.make_prompt_factors(6).items()}
+    fb = {k: v.clone() for k, v in fa.items()}
+    oa, ob = lpi_step.PromptSGD(fa, 0.05), lpi_step.PromptSGD(fb, 0.05)
+    g = lpi_step.GraphedTrainStep(vision, text, fb, ob, images, tokens, 1 / 0.07, text_len=text_len, warmup=2)   # 2 eager warm-up steps; capture records, it does not run
+    for _ in range(2):
+        ra = lpi_step.train_step(vision, text, fa, images, tokens, 1 / 0.07, text_len=text_len)
+        oa.step(ra["grads"])
+    for k in lpi_step.FACTOR_NAMES:
+        assert torch.allclose(fa[k], fb[k], rtol=0, atol=1e-6), k
+    ra = lpi_step.train_step(vision, text, fa, images, tokens, 1 / 0.07, text_len=text_len)
+    oa.step(ra["grads"])
+    rb = g.step()
+    assert abs(float(ra["losses"]["base_loss"]) - float(rb["losses"]["base_loss"])) < 1e-6
+    for k in lpi_step.FACTOR_NAMES:
+        assert torch.allclose(ra["grads"][k], rb["grads"][k], rtol=0, atol=1e-7) and torch.allclose(fa[k], fb[k], rtol=0, atol=1e-6), k
+    images2 = S.make_images(4, 9).cuda()
+    ra = lpi_step.train_step(vision, text, fa, images2, tokens, 1 / 0.07, text_len=text_len)
+    rb = g.step(images2)
+    assert abs(float(ra["losses"]["base_loss"]) - float(rb["losses"]["base_loss"])) < 1e-6

@@ -21,6 +21,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--text-precision", default="fp16")
     ap.add_argument("--fwd-only", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="replay the step from a CUDA graph (lpi_step.GraphedTrainStep)")
     ap.add_argument("--no-trim", action="store_true", help="run the text tower on all 77 positions (default: up to the batch's last EOT)")
     a = ap.parse_args()
     dev = torch.device("cuda")
@@ -42,6 +43,8 @@ def main():
         r = lpi_step.train_step(vision, text, fac, images, tokens, 1 / 0.07, text_len=text_len)
         opt.step(r["grads"])
 
+    if a.graph and not a.fwd_only:
+        step = lpi_step.GraphedTrainStep(vision, text, fac, opt, images, tokens, 1 / 0.07, text_len=text_len).step
     for _ in range(a.warmup):
         step()
     torch.cuda.synchronize()
@@ -58,7 +61,7 @@ def main():
     gflop_pair = 44.05 if a.fwd_only else 89.7
     print(json.dumps({"batch": a.batch, "ms_per_step": ms, "wall_ms_per_step": wall, "pairs_per_s": a.batch / ms * 1e3,
                       "tflops_algorithmic": a.batch * gflop_pair / ms, "launches_per_step": (ops.KERNEL_LAUNCHES - n0) / a.steps,
-                      "text_precision": a.text_precision, "fwd_only": a.fwd_only, "text_positions": text_len or 77}))
+                      "text_precision": a.text_precision, "fwd_only": a.fwd_only, "text_positions": text_len or 77, "graph": bool(a.graph)}))
 
 
 if __name__ == "__main__":
