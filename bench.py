@@ -253,10 +253,13 @@ def run_b200(args):
                 ev.record(cs)
                 evs.append(ev)
         main.wait_event(q_ev)
-        lists_s, lists_i = [], []
+        lists_s, lists_i, thr = [], [], None
         for (a, b), ev in zip(bounds, evs):
             main.wait_event(ev)
-            s_, i_ = ops.sim_topk(q_dev, g_dev[a:b], TOPK, lo + a)
+            # a row of chunk c only matters in the merged list if it beats the best k-th score seen so far: one pre-pass, in chunk 0
+            s_, i_ = ops.sim_topk(q_dev, g_dev[a:b], TOPK, lo + a, init_thr=thr)
+            kth = s_[:, TOPK - 1]
+            thr = kth.contiguous() if thr is None else torch.maximum(thr, kth)      # short lists end in -inf: the running bound stays
             lists_s.append(s_); lists_i.append(i_)
         if len(lists_s) > 1:
             s_, i_ = ops.topk_merge(torch.stack(lists_s), torch.stack(lists_i))

@@ -95,11 +95,15 @@ SEED_MIN_GALLERY = 131072    # below this the warm-up is not worth a second laun
 
 
 def sim_topk(q: torch.Tensor, g: torch.Tensor, k: int = 10, gallery_offset: int = 0, n_chunks: int = 0,
-             merge: bool = True, seed_rows: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+             merge: bool = True, seed_rows: Optional[int] = None, init_thr: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """Top-k gallery rows per query by dot product; q [nq,dim], g [ng,dim] bf16.
     Returns (scores fp32, global idx int32), [nq,k] when merged else [n_chunks,nq,k].
     seed_rows: None = automatic (a pre-pass over the first SEED_ROWS rows of large galleries supplies per-query thresholds, which
-    leaves the result unchanged and removes most sorted insertions), 0 = off, n = pre-pass over the first n rows."""
+    leaves the result unchanged and removes most sorted insertions), 0 = off, n = pre-pass over the first n rows.
+    init_thr: [nq] fp32, per query a score that at least k rows of the same logical gallery are known to reach (e.g. the running
+    maximum of the k-th scores of the chunks of a streamed gallery seen so far); used instead of a pre-pass.  The lists returned then
+    hold only candidates that can still enter the union's top-k (possibly fewer than k; the rest is (-inf, INT_MAX)): merge them with
+    the lists that produced the threshold."""
     _lib.require_device()
     _chk(q, torch.bfloat16, "q")
     _chk(g, torch.bfloat16, "g")
@@ -111,7 +115,12 @@ def sim_topk(q: torch.Tensor, g: torch.Tensor, k: int = 10, gallery_offset: int 
         seed_rows = SEED_ROWS if ng >= SEED_MIN_GALLERY else 0
     seed_rows = min(int(seed_rows), ng)
     thr_ptr, thr_stride, seed_scores = None, 1, None
-    if seed_rows >= k:     # k-th largest per-tile maximum of the sample = the seed (-inf if the sample has fewer than k tiles)
+    if init_thr is not None:
+        _chk(init_thr, torch.float32, "init_thr")
+        if tuple(init_thr.shape) != (nq,):
+            raise _lib.LpiError(f"init_thr must be [{nq}], got {tuple(init_thr.shape)}")
+        thr_ptr, thr_stride = ptr(init_thr), 1
+    elif seed_rows >= k:     # k-th largest per-tile maximum of the sample = the seed (-inf if the sample has fewer than k tiles)
         seed_scores = torch.empty(1, nq, k, device=q.device, dtype=torch.float32)
         seed_idx = torch.empty(1, nq, k, device=q.device, dtype=torch.int32)
         call("sim_topk_seed_bf16", ptr(q), ptr(g), nq, seed_rows, dim, k, ptr(seed_scores), ptr(seed_idx), stream_ptr())

@@ -79,6 +79,26 @@ def test_threshold_seeding_is_exact(order):
     assert torch.equal(i, i1) and torch.equal(v, v1)
 
 
+def test_chained_thresholds_over_gallery_chunks_are_exact():
+    """Streaming a gallery in chunks with each chunk seeded by the best k-th score of the chunks before it (bench.py e2e leg) and merging the
+    lists gives exactly the one-shot result; a chunk's list may legitimately be short."""
+    gen = torch.Generator().manual_seed(23)
+    q = torch.randn(200, 512, generator=gen).bfloat16().cuda()
+    g = torch.randn(30000, 512, generator=gen).bfloat16()
+    g[29000:29010] = g[10:20]                     # ties across chunks: the earlier (lower-index) copy must win
+    g = g.cuda()
+    v0, i0 = ops.sim_topk(q, g, 10, 0, seed_rows=0)
+    ls, li, thr = [], [], None
+    for c in range(5):
+        a, b = c * 6000, (c + 1) * 6000
+        s_, i_ = ops.sim_topk(q, g[a:b], 10, a, seed_rows=0, init_thr=thr)
+        thr = s_[:, 9].contiguous() if thr is None else torch.maximum(thr, s_[:, 9])
+        ls.append(s_); li.append(i_)
+    assert bool((li[-1] == 0x7FFFFFFF).any())                   # later chunks keep fewer than k candidates
+    v, i = ops.topk_merge(torch.stack(ls), torch.stack(li))
+    assert torch.equal(i, i0) and torch.equal(v, v0)
+
+
 def test_topk_rows_and_merge_ties():
     gen = torch.Generator().manual_seed(11)
     s = torch.randn(70, 4001, generator=gen)
