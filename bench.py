@@ -302,7 +302,6 @@ def run_b200(args):
     line_extra = {}
     if rank == 0:
         from oracle import lpi_oracle as O          # checker only (bench cpu_baseline leg)
-        import numpy as np
         assert torch.equal(e2e_counts.cpu(), counts.cpu()), "e2e and device-resident passes disagree"
         if world == 1 and not args.skip_cpu:
             cores = os.cpu_count() or 1

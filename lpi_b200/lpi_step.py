@@ -10,7 +10,7 @@ The nn.Module / autograd mirror of the same maths lives in slinet.py; both call 
 from __future__ import annotations
 
 import os
-from typing import Dict, List, Optional, Sequence
+from typing import Dict, Optional, Sequence
 
 import torch
 

@@ -15,11 +15,11 @@ import json
 import logging
 import os
 from datetime import datetime
-from typing import Dict, List, Optional, Sequence
+from typing import List, Optional, Sequence
 
 import numpy as np
 import torch
-from torch import nn, optim
+from torch import optim
 
 from . import lpi_step, ops, retrieval
 from ._lib import LpiError

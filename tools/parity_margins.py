@@ -4,7 +4,7 @@ import os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-from lpi_b200 import lpi_step, ops, synthetic as S
+from lpi_b200 import lpi_step, synthetic as S
 from lpi_b200.engine import TextEngine, VisionEngine
 
 FACTOR_NAMES = lpi_step.FACTOR_NAMES
