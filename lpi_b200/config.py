@@ -1,6 +1,6 @@
 """Flat-dict run configuration with the reference's keys (retrieval/configs/lpi/coco_lpi.json; argparse + JSON are merged into
 one dict, retrieval/main.py:18-20).  Extra keys understood by this build: inject_layers, group, fused_step, n_tasks,
-clip_state_dict, task_loaders, checkpoint_dir, resume_from."""
+clip_state_dict, task_loaders, checkpoint_dir, resume_from, graph_step."""
 from __future__ import annotations
 
 

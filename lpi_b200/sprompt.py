@@ -91,6 +91,29 @@ class FusedSGD(optim.Optimizer):
                                       group["weight_decay"], first)
 
 
+class _CapturedStep:
+    """A closure over static input buffers captured into a CUDA graph (all graphs of a learner share one memory pool: they replay one
+    at a time).  Calling it copies the new inputs into the captured buffers and replays; the returned tensors are the captured outputs."""
+
+    def __init__(self, fn, static_inputs: dict, owner: "SPrompts"):
+        self.inputs = static_inputs
+        if owner._graph_pool is None:
+            owner._graph_pool = torch.cuda.graph_pool_handle()
+        torch.cuda.synchronize()
+        n0 = ops.KERNEL_LAUNCHES
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, pool=owner._graph_pool):
+            self.out = fn(**self.inputs)
+        self.launches = ops.KERNEL_LAUNCHES - n0
+
+    def __call__(self, **new_inputs):
+        for k, v in new_inputs.items():
+            self.inputs[k].copy_(v, non_blocking=True)
+        self.graph.replay()
+        ops._count(self.launches)
+        return self.out
+
+
 class SPrompts(object):
     def __init__(self, args):
         # BaseLearner fields (base.py:14-28)
@@ -117,6 +140,11 @@ class SPrompts(object):
         self.cur_id = 0
         self.group = args.get("group")                    # torch.distributed process group for data-parallel training
         self.fused_step = bool(args.get("fused_step", True))
+        # opt-in: replay the fused step from CUDA graphs (one per batch shape / text-length bucket / learning rate, see _step_fused)
+        self.graph_step = bool(args.get("graph_step", False))
+        self._graphs: dict = {}
+        self._graph_pool = None
+        self._task_consts: dict = {}
         self.n_tasks = int(args.get("n_tasks", args["total_sessions"]))
         self.log = logging.getLogger("lpi_b200")
 
@@ -187,6 +215,8 @@ class SPrompts(object):
         with torch.no_grad():
             for k, v in st["trainable"].items():
                 own[k].copy_(v.to(own[k].device, own[k].dtype))
+        self._task_consts.clear()
+        self._graphs.clear()
         self._network.numtask = st["numtask"]
         self.cur_id = st["cur_id"]
         self._cur_task = [self.cur_id]
@@ -200,6 +230,8 @@ class SPrompts(object):
             json.dump(dictionary, f)
 
     def _train(self, train_loader, test_loader):
+        self._task_consts.clear()                              # per-task caches of the fused step (earlier prompts may have been reloaded)
+        self._graphs.clear()
         self._network.to(self._device)
         network = self._network
         for name, param in network.named_parameters():          # freeze all but "prompts.{t}." (sprompt.py:229-237)
@@ -221,27 +253,61 @@ class SPrompts(object):
         optimizer.step()
         return model_out["loss"]
 
+    def _task_constants(self, net, device):
+        """Per-task constants of the fused step, computed once per task instead of once per step: exp(logit_scale) (a device -> host
+        read), the reconstructed prompts of the frozen earlier tasks, the task-similarity targets (slinet.py:167-183)."""
+        key = (net.numtask, str(device))
+        c = self._task_consts.get(key)
+        if c is None:
+            t = net.numtask - 1
+            prev, target = [], None
+            if net.numtask != 1:
+                with torch.no_grad():
+                    prev = [net.prompts[i]() for i in range(t)]
+                sim = load_task_sim_matrix() if net._task_sim is None else net._task_sim
+                net._task_sim = sim
+                target = torch.tensor((sim[:t + 1, :t + 1] > L.TASK_THRESHOLD).astype(np.int32), device=device)
+            c = self._task_consts[key] = (float(net.logit_scale.exp()), prev, target)
+        return c
+
     def _step_fused(self, images, captions, optimizer):
-        """Same maths as _step_autograd without the autograd graph; supports the data-parallel group."""
+        """Same maths as _step_autograd without the autograd graph; supports the data-parallel group.  With args['graph_step'] the
+        step is replayed from a CUDA graph from the second occurrence of a (batch shape, text-length bucket, learning rate) on."""
         net = self._network
         t = net.numtask - 1
         prompt = net.prompts[t]
         factors = {k: getattr(prompt, k).data for k in lpi_step.FACTOR_NAMES}
         tokens = captions if isinstance(captions, torch.Tensor) else net.classifier_pool[t].tokenize(captions)
-        prev, target = [], None
-        if net.numtask != 1:
-            with torch.no_grad():
-                prev = [net.prompts[i]() for i in range(t)]
-            sim = load_task_sim_matrix() if net._task_sim is None else net._task_sim
-            net._task_sim = sim
-            target = torch.tensor((sim[:t + 1, :t + 1] > L.TASK_THRESHOLD).astype(np.int32), device=images.device)
-        r = lpi_step.train_step(net.image_encoder.engine(), net.clip_model.text_engine(), factors, images.float(), tokens,
-                                float(net.logit_scale.exp()), prev, target, tuple(net.clip_model.inject_layers), self.group)
+        scale, prev, target = self._task_constants(net, images.device)
+        vision, text = net.image_encoder.engine(), net.clip_model.text_engine()
+        inject = tuple(net.clip_model.inject_layers)
+        text_len = getattr(tokens, "lpi_text_len", None)
+
+        def run(images, tokens, text_len):
+            r = lpi_step.train_step(vision, text, factors, images, tokens, scale, prev, target, inject, self.group, text_len=text_len)
+            for k in lpi_step.FACTOR_NAMES:
+                getattr(prompt, k).grad = r["grads"][k]
+            optimizer.step()
+            return {k: v.view(()) for k, v in r["losses"].items()}
+
+        images = images.float()
+        if self.graph_step:
+            # a longer text_len is still exact, so lengths are bucketed to multiples of 8 to bound the number of graphs
+            tl = tokens.shape[1] if text_len is None else min(tokens.shape[1], -(-int(text_len) // 8) * 8)
+            lr = float(optimizer.param_groups[0]["lr"])
+            key = (net.numtask, tuple(images.shape), tuple(tokens.shape), tl, lr)
+            slot = self._graphs.get(key)
+            if slot is None:                                   # first occurrence: eager (it is also the warm-up of every lazy one-time setup)
+                for k in [k for k in self._graphs if k[0] != net.numtask or k[-1] != lr]:
+                    del self._graphs[k]                        # graphs of earlier tasks / learning rates are dead
+                self._graphs[key] = "seen"
+            else:
+                if slot == "seen":
+                    slot = self._graphs[key] = _CapturedStep(lambda images, tokens: run(images, tokens, tl),
+                                                             dict(images=images.clone(), tokens=tokens.clone()), self)
+                return slot(images=images, tokens=tokens)
         optimizer.zero_grad()
-        for k in lpi_step.FACTOR_NAMES:
-            getattr(prompt, k).grad = r["grads"][k]
-        optimizer.step()
-        return {k: v.view(()) for k, v in r["losses"].items()}
+        return run(images, tokens, text_len)
 
     def train_function(self, train_loader, test_loader, optimizer, scheduler):
         """sprompt.py:290-334"""

@@ -168,3 +168,31 @@ def test_incremental_train_checkpoint_and_resume(clip_sd, tmp_path, monkeypatch)
     summary = RH.summarize(json.load(open(files[-1])), "mscoco", "i2t")
     assert set(summary["per_task"]) == {0, 1, 2} and summary["per_task"][0]["sessions"] == 3
     assert summary["final"][2] == res_a[2]["mscoco"]["i2t"][2]
+
+
+def test_learner_graph_replay_equals_eager(clip_sd, tmp_path, monkeypatch):
+    """args['graph_step']: the fused step replayed from CUDA graphs (captured on the second occurrence of a batch shape / text-length
+    bucket / learning rate; two epochs so the cosine schedule forces a re-capture) must leave the learner in the eager learner's state."""
+    monkeypatch.chdir(tmp_path)
+    n_tasks = 2
+
+    def run(graph):
+        torch.manual_seed(0)
+        args = default_args(clip_state_dict=clip_sd, device=[torch.device("cuda")], epochs=2, batch_size=8, n_tasks=n_tasks, graph_step=graph)
+        learner = SPrompts(args)
+        with torch.no_grad():
+            for t in range(n_tasks):
+                for k, v in S.make_prompt_factors(t).items():
+                    getattr(learner._network.prompts[t], k).copy_(v)
+        res = learner.incremental_train(D.make_task_loaders(n_tasks, 32, 6, 2, 8, 8))
+        return learner, res
+
+    a, res_a = run(False)
+    b, res_b = run(True)
+    from lpi_b200.sprompt import _CapturedStep
+
+    assert any(isinstance(v, _CapturedStep) for v in b._graphs.values())                    # graphs were actually captured and replayed
+    assert res_a == res_b
+    for t in range(n_tasks):
+        for k in O.FACTOR_NAMES:
+            assert torch.allclose(getattr(a._network.prompts[t], k), getattr(b._network.prompts[t], k), rtol=0, atol=2e-6), (t, k)
