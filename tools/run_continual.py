@@ -17,12 +17,14 @@ def main():
     ap.add_argument("--epochs", type=int, default=2)
     ap.add_argument("--eval-images", type=int, default=100)
     ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--graph", action="store_true", help="replay the fused step from CUDA graphs (args['graph_step'])")
     a = ap.parse_args()
     work = tempfile.mkdtemp(prefix="lpi_continual_")
     os.chdir(work)
+    torch.manual_seed(0)                               # the prompt factors are drawn from torch's global generator (prompts.py:21-25)
     sd = S.make_clip_state_dict(0)
     args = default_args(clip_state_dict=sd, device=[torch.device("cuda")], epochs=a.epochs, batch_size=a.batch, n_tasks=a.tasks,
-                        checkpoint_dir=os.path.join(work, "ckpt"))
+                        checkpoint_dir=os.path.join(work, "ckpt"), graph_step=a.graph)
     learner = SPrompts(args)
     loaders = D.make_task_loaders(a.tasks, a.train, a.eval_images, 5, a.batch, 128)
     torch.cuda.synchronize()
@@ -31,7 +33,7 @@ def main():
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     out = {"config": "5-task continual retrieval sequence (BASELINE.json configs[3])", "tasks": a.tasks, "train_pairs_per_task": a.train,
-           "epochs": a.epochs, "eval_images_per_task": a.eval_images, "captions_per_image": 5, "wall_s": dt,
+           "epochs": a.epochs, "graph_step": a.graph, "eval_images_per_task": a.eval_images, "captions_per_image": 5, "wall_s": dt,
            "lpi_kernel_launches": ops.KERNEL_LAUNCHES - n0,
            "final_session": {side: res[a.tasks - 1]["mscoco"][side] for side in ("i2t", "t2i")},
            "summary_i2t": RH.summarize(res, "mscoco", "i2t"), "summary_t2i": RH.summarize(res, "mscoco", "t2i"),
