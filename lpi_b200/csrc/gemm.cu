@@ -43,6 +43,7 @@ struct GemmArgs {
     float* out2_f32;               // [M, ldo] fp32 pre-activation (EPI_BIAS_GELU_F32)
     const float* aux_f32;          // [M, ldo] fp32 pre-activation (EPI_DGELU_F32)
     int ldo;
+    int probe;                     // debug (LPI_GEMM_PROBE): 1 = the pair GEMM skips its A-tile loads (WRONG results; measures how much the smem fill costs)
     int precise_act;               // fp16 outputs: 1 = ex2 + rcp sigmoid (2 MUFU ops), 0 = tanh.approx (1 MUFU op, |err| <= 2^-12)
     // MODE_TOPK
     int k;                         // top-k (<= TOPK_MAX)
@@ -656,10 +657,11 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     const int n0 = nt * BN + int(rank) * 128;       // this CTA streams its half of the B tile
                     for (int kb = 0; kb < num_k; ++kb) {
                         mbar_wait(empty_bar(stage), phase ^ 1);
-                        if (leader) mbar_arrive_expect_tx(full_bar(stage), 2u * C::STAGE_BYTES);
+                        const bool skip_a = (MODE == MODE_GEMM) && p.probe == 1;
+                        if (leader) mbar_arrive_expect_tx(full_bar(stage), skip_a ? 2u * C::BH_BYTES : 2u * C::STAGE_BYTES);
                         const uint32_t sa = smem_base + C::RING_OFF + stage * C::STAGE_BYTES;
                         if (MODE == MODE_GEMM) {
-                            tma_load_2d_pair(sa, &tmA, full_bar(stage), kb * BKE, m0);
+                            if (!skip_a) tma_load_2d_pair(sa, &tmA, full_bar(stage), kb * BKE, m0);
                             tma_load_2d_pair(sa + C::A_BYTES, &tmB, full_bar(stage), kb * BKE, n0);
                         } else {
                             tma_load_2d_pair(sa, &tmB, full_bar(stage), kb * BKE, n0);
@@ -985,6 +987,12 @@ static int gemm_entry(int op, const void* A, const void* B, int M, int N, int K,
             precise = (e && e[0] == '1') ? 1 : 0;
         }
         a.precise_act = precise;
+        static int probe = -1;
+        if (probe < 0) {
+            const char* e = getenv("LPI_GEMM_PROBE");
+            probe = e ? atoi(e) : 0;
+        }
+        a.probe = probe;
     }
     a.bias = static_cast<const float*>(bias);
     a.resid = static_cast<const float*>(resid);
