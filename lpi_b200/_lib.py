@@ -10,7 +10,7 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "liblpi_b200.so")
+LIB_PATH = os.environ.get("LPI_LIB_PATH") or os.path.join(_HERE, "liblpi_b200.so")      # override: A/B runs of two builds on one box
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "lpi_b200.h")
 
 _lib = None

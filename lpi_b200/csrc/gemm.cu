@@ -28,6 +28,9 @@ constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 constexpr int GEMM_THREADS = 192;
 constexpr int TOPK_MAX = 16;
+#ifndef LPI_EPI16
+#define LPI_EPI16 1          // 16-bit staging of 16-bit outputs in the pair GEMM epilogue (0 = the fp32 transpose for every epilogue)
+#endif
 
 enum { MODE_GEMM = 0, MODE_TOPK = 1 };
 
@@ -255,6 +258,53 @@ __device__ __forceinline__ void epilogue_block(const GemmArgs& p, const float4* 
             *reinterpret_cast<uint2*>(p.out_bf16 + off) = make_uint2(pack_h2<F16>(v[i].x, v[i].y), pack_h2<F16>(v[i].z, v[i].w));
         }
     }
+}
+
+// 16-bit-output epilogues without an aux / residual operand (EPI_BIAS_BF16, EPI_BF16, EPI_BIAS_GELU_BF16): bias and activation are applied
+// in the accumulator layout (thread = row; the bias read is a warp-wide broadcast) and the block is transposed through shared memory as
+// 16-bit values -- 2 KB per 32x32 block instead of 4 KB of fp32, i.e. half the smem traffic the probe in DESIGN.md section 8 points at.
+// Row r of the block occupies 64 B = four 16-byte chunks, chunk q stored at slot q ^ ((r >> 1) & 3): both directions are conflict-free.
+template <int EPI, bool F16>
+__device__ __forceinline__ void epilogue_block16(const GemmArgs& p, const uint32_t (&r)[32], uint4* __restrict__ st, int row0, int col0, int lane) {
+    const int rows = min(32, p.M - row0);                      // warp-uniform
+    if (rows <= 0) return;
+    constexpr bool kBias = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16);
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (kBias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 4 * j));
+        v[4 * j] = __uint_as_float(r[4 * j]) + b4.x;
+        v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b4.y;
+        v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b4.z;
+        v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b4.w;
+    }
+    const int sw = (lane >> 1) & 3;
+    auto stage_and_store = [&](__nv_bfloat16* dst) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            st[lane * 4 + (q ^ sw)] = make_uint4(pack_h2<F16>(v[8 * q], v[8 * q + 1]), pack_h2<F16>(v[8 * q + 2], v[8 * q + 3]),
+                                                 pack_h2<F16>(v[8 * q + 4], v[8 * q + 5]), pack_h2<F16>(v[8 * q + 6], v[8 * q + 7]));
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int rr = it * 8 + (lane >> 2), q = lane & 3;
+            const uint4 w = st[rr * 4 + (q ^ ((rr >> 1) & 3))];
+            if (rr < rows) *reinterpret_cast<uint4*>(dst + size_t(row0 + rr) * p.ldo + col0 + q * 8) = w;
+        }
+        __syncwarp();
+    };
+    if (EPI == EPI_BIAS_GELU_BF16) {
+        if (p.out2_bf16) stage_and_store(p.out2_bf16);          // pre-activation, kept for the backward
+        if (F16 && p.precise_act) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = quick_gelu<true>(v[j]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = quick_gelu<false>(v[j]);
+        }
+    }
+    stage_and_store(p.out_bf16);
 }
 
 // The saved pre-activation read by the dGELU epilogue was written a whole forward pass earlier, i.e. it comes from DRAM: loaded
@@ -750,13 +800,18 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         LPI_TMEM_LD_X32(taddr, r);
                         tmem_ld_wait();
                         float4* stg = reinterpret_cast<float4*>(smem_gen + C::LIST_OFF) + (warp - 2) * 32 * 8;
+                        constexpr bool k16 = (EPI == EPI_BIAS_BF16 || EPI == EPI_BF16 || EPI == EPI_BIAS_GELU_BF16) && LPI_EPI16;
+                        if (k16) {
+                            epilogue_block16<EPI, F16>(p, r, reinterpret_cast<uint4*>(stg), m0 + quad * 32, n0 + c * 32, lane);
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            stg[lane * 8 + (j ^ (lane & 7))] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                                                           __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-                        __syncwarp();
-                        epilogue_block<EPI, F16>(p, stg, m0 + quad * 32, n0 + c * 32, lane, pre);
-                        __syncwarp();
+                            for (int j = 0; j < 8; ++j)
+                                stg[lane * 8 + (j ^ (lane & 7))] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                                               __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+                            __syncwarp();
+                            epilogue_block<EPI, F16>(p, stg, m0 + quad * 32, n0 + c * 32, lane, pre);
+                            __syncwarp();
+                        }
                     };
                     if (kPrefetchAux) {
                         static_assert(NCH == 4, "the aux prefetch schedule below is written for 4 blocks per warp");
