@@ -156,6 +156,7 @@ int lpi_layernorm_bwd_dy16(const void* dy16, int is_f16, const float* x, const f
  * assemble_bwd: d_prompt[t,p,:] = sum_{b: sel[b]=t} dLN(g[b,1+p,:]; prompt_table[t,p,:], ln_pre.weight)   (overwrites d_prompt)
  * ------------------------------------------------------------------------------------------------ */
 int lpi_im2col_patches(const float* images, void* out_bf16, int B, int resolution, int patch, void* stream);
+int lpi_im2col_patches_f16(const float* images, void* out_f16, int B, int resolution, int patch, void* stream);   /* fp16 vision tower */
 int lpi_assemble_vision(const float* patch_emb, const float* cls, const float* pos, const float* prompt_table, const int* sel,
                         const float* ln_gamma, const float* ln_beta, float* x_out, int B, int n_patch, int P, int D, float eps,
                         void* stream);

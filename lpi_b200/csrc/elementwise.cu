@@ -146,6 +146,7 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const float* 
 
 // ------------------------------------------------------------------------------------------------ vision front end
 // images [B,3,R,R] fp32 -> patch rows [B*G*G, 3*P*P] bf16, column = c*P*P + i*P + j (conv1.weight.view(D,-1) order)
+template <bool F16>
 __global__ void im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int R, int P) {
     const int G = R / P, K = 3 * P * P;
     const long n = long(B) * G * G * K / 4;          // 4 consecutive j per thread (P % 4 == 0)
@@ -157,7 +158,7 @@ __global__ void im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __re
     const int gx = int(prow % G), gy = int((prow / G) % G), b = int(prow / (G * G));
     const int c = col / (P * P), i = (col / P) % P, j = col % P;
     const float4 v = *reinterpret_cast<const float4*>(img + ((long(b) * 3 + c) * R + gy * P + i) * R + gx * P + j);
-    *reinterpret_cast<uint2*>(out + e) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+    *reinterpret_cast<uint2*>(out + e) = make_uint2(pack_h2<F16>(v.x, v.y), pack_h2<F16>(v.z, v.w));
 }
 
 // Token assembly + ln_pre (model.py:235-250).  Row l of sample b:
@@ -501,14 +502,23 @@ extern "C" int lpi_layernorm_bwd(const float* dy, const float* x, const float* g
     return rc ? rc : check_launch("layernorm_bwd");
 }
 
-extern "C" int lpi_im2col_patches(const float* images, void* out_bf16, int B, int resolution, int patch, void* stream) {
+static int im2col_entry(const float* images, void* out16, bool f16, int B, int resolution, int patch, void* stream) {
     if (B <= 0) return LPI_OK;
     if (patch % 4 || resolution % patch) return set_error(LPI_ERR_ARG, "im2col: bad resolution %d / patch %d", resolution, patch);
     const int G = resolution / patch;
     const long n = long(B) * G * G * 3 * patch * patch / 4;
-    im2col_kernel<<<unsigned((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(images, static_cast<__nv_bfloat16*>(out_bf16), B,
-                                                                                           resolution, patch);
+    auto* out = static_cast<__nv_bfloat16*>(out16);
+    if (f16) im2col_kernel<true><<<unsigned((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(images, out, B, resolution, patch);
+    else im2col_kernel<false><<<unsigned((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(images, out, B, resolution, patch);
     return check_launch("im2col");
+}
+
+extern "C" int lpi_im2col_patches(const float* images, void* out_bf16, int B, int resolution, int patch, void* stream) {
+    return im2col_entry(images, out_bf16, false, B, resolution, patch, stream);
+}
+
+extern "C" int lpi_im2col_patches_f16(const float* images, void* out_f16, int B, int resolution, int patch, void* stream) {
+    return im2col_entry(images, out_f16, true, B, resolution, patch, stream);
 }
 
 extern "C" int lpi_assemble_vision(const float* patch_emb, const float* cls, const float* pos, const float* prompt_table, const int* sel,

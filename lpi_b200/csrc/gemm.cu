@@ -18,6 +18,7 @@
 #include "ptx.cuh"
 #include "lpi_internal.h"
 #include <cuda_fp16.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 namespace lpi {
@@ -46,7 +47,7 @@ struct GemmArgs {
     float* out2_f32;               // [M, ldo] fp32 pre-activation (EPI_BIAS_GELU_F32)
     const float* aux_f32;          // [M, ldo] fp32 pre-activation (EPI_DGELU_F32)
     int ldo;
-    int probe;                     // debug (LPI_GEMM_PROBE): 1 = the pair GEMM skips its A-tile loads (WRONG results; measures how much the smem fill costs)
+    int probe;                     // only in -DLPI_DEBUG_PROBE builds (tools/gemm_probe.py): 1 = the pair GEMM skips its A-tile loads (WRONG results, timing study)
     int precise_act;               // fp16 outputs: 1 = ex2 + rcp sigmoid (2 MUFU ops), 0 = tanh.approx (1 MUFU op, |err| <= 2^-12)
     // MODE_TOPK
     int k;                         // top-k (<= TOPK_MAX)
@@ -707,7 +708,11 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     const int n0 = nt * BN + int(rank) * 128;       // this CTA streams its half of the B tile
                     for (int kb = 0; kb < num_k; ++kb) {
                         mbar_wait(empty_bar(stage), phase ^ 1);
+#ifdef LPI_DEBUG_PROBE
                         const bool skip_a = (MODE == MODE_GEMM) && p.probe == 1;
+#else
+                        constexpr bool skip_a = false;
+#endif
                         if (leader) mbar_arrive_expect_tx(full_bar(stage), skip_a ? 2u * C::BH_BYTES : 2u * C::STAGE_BYTES);
                         const uint32_t sa = smem_base + C::RING_OFF + stage * C::STAGE_BYTES;
                         if (MODE == MODE_GEMM) {
@@ -1022,7 +1027,7 @@ static int gemm_entry(int op, const void* A, const void* B, int M, int N, int K,
     const int sms = num_sms();
     if (bn == 0) {
         // CTA-pair 256 x 256 tiles whenever N allows: they measured at or above the 1-CTA tiles on every encoder shape
-        // (profiles/r1_gemm_microbench_v2.txt); otherwise the narrow 1-CTA tile.
+        // (profiles/r2_gemm_microbench.txt); otherwise the narrow 1-CTA tile.
         bn = (N % 256 == 0) ? 512 : 128;
     }
     const bool pair = (bn == 512);               // CTA-pair kernel: 256 x 256 tile over two SMs (cta_group::2)
@@ -1042,12 +1047,16 @@ static int gemm_entry(int op, const void* A, const void* B, int M, int N, int K,
             precise = (e && e[0] == '1') ? 1 : 0;
         }
         a.precise_act = precise;
+#ifdef LPI_DEBUG_PROBE
+        // timing-study build only (never the shipped library): a stray environment variable must not be able to corrupt results
         static int probe = -1;
         if (probe < 0) {
             const char* e = getenv("LPI_GEMM_PROBE");
             probe = e ? atoi(e) : 0;
+            if (probe) fprintf(stderr, "[lpi_b200] LPI_GEMM_PROBE=%d: GEMM RESULTS ARE WRONG (timing study build)\n", probe);
         }
         a.probe = probe;
+#endif
     }
     a.bias = static_cast<const float*>(bias);
     a.resid = static_cast<const float*>(resid);

@@ -210,19 +210,32 @@ class Tower:
 
 
 # ------------------------------------------------------------------------------------------------ image encoder
+DEFAULT_VISION_PRECISION = "bf16"
+
+
 class VisionEngine:
     """VisionTransformer.forward (model.py:227-259) on the kernels: im2col -> patch GEMM -> assemble(+ln_pre) -> tower -> head."""
 
-    def __init__(self, sd: Dict[str, torch.Tensor], dev, prefix: str = "visual.", need_grad: bool = True):
+    def __init__(self, sd: Dict[str, torch.Tensor], dev, prefix: str = "visual.", need_grad: bool = True, precision: Optional[str] = None):
+        """precision: 'bf16' or 'fp16' GEMM / attention operands (fp32 accumulation, residual stream, LayerNorm and head either way);
+        None = $LPI_VISION_PRECISION or the default below.  fp16 carries 3 more mantissa bits at the same tensor rate and is the
+        reference's own GPU dtype (convert_weights, model.py:394-415); its gradient stream is scaled by 2^10 (Tower.grad_scale)."""
+        import os
+
+        precision = precision or os.environ.get("LPI_VISION_PRECISION", DEFAULT_VISION_PRECISION)
+        if precision not in ("bf16", "fp16"):
+            raise ValueError(f"vision precision must be 'bf16' or 'fp16', got {precision!r}")
+        self.precision = precision
+        self.half = torch.float16 if precision == "fp16" else torch.bfloat16
         w = sd[prefix + "conv1.weight"]
         self.width, _, self.patch, _ = w.shape
-        self.conv_w = _bf16(w.reshape(self.width, -1), dev)
+        self.conv_w = _half(w.reshape(self.width, -1), dev, self.half)
         self.cls = _f32(sd[prefix + "class_embedding"], dev)
         self.pos = _f32(sd[prefix + "positional_embedding"], dev)
         self.ln_pre = (_f32(sd[prefix + "ln_pre.weight"], dev), _f32(sd[prefix + "ln_pre.bias"], dev))
         self.ln_post = (_f32(sd[prefix + "ln_post.weight"], dev), _f32(sd[prefix + "ln_post.bias"], dev))
         self.proj = _f32(sd[prefix + "proj"], dev)
-        self.tower = Tower(sd, prefix + "transformer.resblocks.", self.width // 64, False, dev, need_grad)
+        self.tower = Tower(sd, prefix + "transformer.resblocks.", self.width // 64, False, dev, need_grad, precision)
         self.n_patch = self.pos.shape[0] - 1
         self.dev = dev
 
@@ -232,7 +245,7 @@ class VisionEngine:
         sel int32[B] picks the table per sample (None = table 0).  Returns (L2-normalised features, raw projection z), both [B, E] fp32."""
         B = images.shape[0]
         D = self.width
-        patches = ops.im2col_patches(images.contiguous(), self.patch)
+        patches = ops.im2col_patches(images.contiguous(), self.patch, self.half)
         pe = ops.gemm(patches, self.conv_w, ops.EPI_F32)
         P = 0 if prompt_table is None else prompt_table.shape[2]
         layer0 = None if prompt_table is None else prompt_table[:, 0].contiguous()

@@ -294,14 +294,14 @@ def layernorm_bwd(dy, x, gamma, g, g_bf16=None, accumulate=True, grad_scale: Opt
     return g
 
 
-def im2col_patches(images: torch.Tensor, patch: int) -> torch.Tensor:
+def im2col_patches(images: torch.Tensor, patch: int, half_dtype=torch.bfloat16) -> torch.Tensor:
     _lib.require_device()
     _chk(images, torch.float32, "images")
     B, ch, R, _ = images.shape
     assert ch == 3
     G = R // patch
-    out = torch.empty(B * G * G, 3 * patch * patch, device=images.device, dtype=torch.bfloat16)
-    call("im2col_patches", ptr(images), ptr(out), B, R, patch, stream_ptr())
+    out = torch.empty(B * G * G, 3 * patch * patch, device=images.device, dtype=half_dtype)
+    call("im2col_patches_f16" if half_dtype == torch.float16 else "im2col_patches", ptr(images), ptr(out), B, R, patch, stream_ptr())
     _count()
     return out
 

@@ -42,10 +42,14 @@ def run() -> None:
     want = gold["step_task1"]
     rel = lambda a, b: float((a.double().cpu() - b.double()).norm() / b.double().norm())
     assert rel(r["img_f"], want["img_f"]) < 1e-2 and rel(r["txt_f"], want["txt_f"]) < 1e-2, "feature parity"
+    lg_err = rel(r["logits"], want["logits"])
+    lg_cos = float((r["logits"].double().cpu() - want["logits"].double()).abs().max()) * 0.07
+    assert lg_err < 1e-2 and lg_cos < 1e-2, f"logits parity: Frobenius-relative {lg_err:.2e}, max-abs / logit_scale {lg_cos:.2e}"
     for k2, v2 in want["losses"].items():
         assert abs(float(r["losses"][k2]) - v2) < 1e-2 * max(abs(v2), 1e-3), f"loss {k2}"
     worst = max(rel(r["grads"][k2], want["grads"][k2]) for k2 in O.FACTOR_NAMES)
     assert worst < 2e-2, f"prompt-gradient parity {worst}"
     torch.cuda.synchronize()
-    print("train step ok: base_loss %.4f, worst prompt-grad rel err %.2e" % (float(r["losses"]["base_loss"]), worst))
+    print("train step ok: base_loss %.4f, logits rel err %.2e (max-abs/scale %.2e), worst prompt-grad rel err %.2e"
+          % (float(r["losses"]["base_loss"]), lg_err, lg_cos, worst))
     print("smoke ok: Recall@K bit-exact vs oracle; gemm max err %.3e; lpi kernels launched: %d" % (err, ops.KERNEL_LAUNCHES))

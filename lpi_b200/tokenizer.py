@@ -5,9 +5,10 @@ Behavioural mirror of the reference's `clip.tokenize` / `SimpleTokenizer`
 text -> byte-level BPE with the 48 894 OpenAI merges -> [SOT] ids [EOT] zero-padded to 77, RuntimeError if longer.
 Tokenisation is host work, not a GPU job; captions are tokenised once and the ids cached by the callers.
 
-The merge table is the data file `bpe_simple_vocab_16e6.txt.gz` shipped with CLIP.  It is looked up, in order, at
-$LPI_BPE_VOCAB, lpi_b200/data/, and oracle/_ref/ (where build() stages it when the reference tree is mounted).
-`ftfy.fix_text` is applied when ftfy is installed (identity on ASCII captions otherwise).
+The merge table is the data file `bpe_simple_vocab_16e6.txt.gz` shipped with CLIP (a constant table, byte-identical to the
+reference's copy); it ships inside the package at lpi_b200/data/ and can be overridden with $LPI_BPE_VOCAB.
+`ftfy.fix_text` is applied when ftfy is installed.  It is the identity on ASCII captions; without ftfy a non-ASCII caption could
+tokenise differently from the reference, so that case warns once instead of diverging silently.
 """
 from __future__ import annotations
 
@@ -25,12 +26,11 @@ VOCAB_NAME = "bpe_simple_vocab_16e6.txt.gz"
 
 
 def find_vocab() -> str:
-    cands = [os.environ.get("LPI_BPE_VOCAB"), os.path.join(_HERE, "data", VOCAB_NAME),
-             os.path.join(os.path.dirname(_HERE), "oracle", "_ref", VOCAB_NAME)]
+    cands = [os.environ.get("LPI_BPE_VOCAB"), os.path.join(_HERE, "data", VOCAB_NAME)]
     for c in cands:
         if c and os.path.isfile(c):
             return c
-    raise FileNotFoundError(f"{VOCAB_NAME} not found (set LPI_BPE_VOCAB or run __graft_entry__.build() where the reference is mounted)")
+    raise FileNotFoundError(f"{VOCAB_NAME} not found under lpi_b200/data/ (or $LPI_BPE_VOCAB)")
 
 
 @lru_cache()
@@ -48,13 +48,22 @@ def _byte_table() -> Dict[int, str]:
     return table
 
 
+_WARNED_FTFY = False
+
+
 def _clean(text: str) -> str:
     try:
         import ftfy
 
         text = ftfy.fix_text(text)
     except ImportError:
-        pass
+        global _WARNED_FTFY
+        if not _WARNED_FTFY and not text.isascii():
+            import warnings
+
+            warnings.warn("lpi_b200.tokenizer: ftfy is not installed; non-ASCII captions skip ftfy.fix_text and may tokenise "
+                          "differently from the reference (simple_tokenizer.py:51)", RuntimeWarning, stacklevel=3)
+            _WARNED_FTFY = True
     text = html.unescape(html.unescape(text)).strip()
     return re.sub(r"\s+", " ", text).strip()
 

@@ -1,7 +1,9 @@
 """Golden fixture for the whole-learner path (BASELINE.json configs[3], scaled down): the REAL reference SPrompts learner run
 on CPU for 2 synthetic tasks (16 train pairs, batch 8, 2 epochs; 6 eval images x 2 captions per task).  Only the 12-task
 `for` of incremental_train is restated (it hard-codes COCO files, sprompt.py:154-172); _train -> train_function -> clustering
--> _evaluate_retrieval -> itm_eval run untouched.     python tests/golden/make_golden_learner.py   (build container only)"""
+-> _evaluate_retrieval -> itm_eval run untouched.     python tests/golden/make_golden_learner.py [n_tasks]  (build container only)
+n_tasks = 2 (default) -> learner_2task_seed0.pt; n_tasks = 5 -> learner_5task_seed0.pt, the 5-task continual sequence of
+BASELINE.json configs[3] (per-task prompt growth, task loss over 2..5 stacked prompts, evaluation over tasks 0..t after every task)."""
 import os
 import sys
 
@@ -19,6 +21,8 @@ CFG = dict(n_tasks=2, n_train=16, n_eval_images=6, caps_per_image=2, batch_size=
 
 
 def main():
+    if len(sys.argv) > 1:
+        CFG["n_tasks"] = int(sys.argv[1])
     torch.manual_seed(0)
     torch.set_num_threads(os.cpu_count())
     ns = RL.load_reference()
@@ -66,7 +70,7 @@ def main():
             "sel_i": sel_i.clone(), "sel_t": sel_t.clone(), "img_f": f_i.clone(), "txt_f": f_t.clone(),
         })
         print("task", t, res, step_log[-1])
-    torch.save(g, os.path.join(OUT, "learner_2task_seed0.pt"))
+    torch.save(g, os.path.join(OUT, f"learner_{CFG['n_tasks']}task_seed0.pt"))
 
 
 if __name__ == "__main__":

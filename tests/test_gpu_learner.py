@@ -69,10 +69,13 @@ def test_slinet_autograd_path_matches_reference(clip_sd, golden_model):
         assert _rel(net.textual_interface(captions, g["interface_cat"]), g["textual_interface"]) < 1e-2
 
 
-@pytest.mark.parametrize("fused", [True, False])
-def test_learner_two_tasks_matches_reference(clip_sd, fused, tmp_path, monkeypatch):
+@pytest.mark.parametrize("fused,fixture", [(True, "learner_2task_seed0.pt"), (False, "learner_2task_seed0.pt"),
+                                           (True, "learner_5task_seed0.pt")])
+def test_learner_tasks_match_reference(clip_sd, fused, fixture, tmp_path, monkeypatch):
+    """The whole learner against the REAL reference learner's run log: 2 tasks (both step implementations) and the 5-task continual
+    sequence of BASELINE.json configs[3] (prompt growth per task, task loss over 2..5 stacked prompts, evaluation over tasks 0..t)."""
     monkeypatch.chdir(tmp_path)
-    g = torch.load(os.path.join(GOLDEN, "learner_2task_seed0.pt"), weights_only=False)
+    g = torch.load(os.path.join(GOLDEN, fixture), weights_only=False)
     cfg = g["cfg"]
     args = default_args(clip_state_dict=clip_sd, device=[torch.device("cuda")], epochs=cfg["epochs"], batch_size=cfg["batch_size"],
                         fused_step=fused, n_tasks=cfg["n_tasks"])
@@ -117,9 +120,16 @@ def test_learner_two_tasks_matches_reference(clip_sd, fused, tmp_path, monkeypat
             imgs = torch.stack(ds.image).cuda()
             sel_i = learner.get_visual_task_id(imgs)
             sel_t = learner.get_textual_task_id(ds.text)
+            # the task-id kernel on OUR un-prompted features against the REFERENCE's keys: isolates a13 from the K-Means initialisation
+            ref_keys_i = [x["keys_visual"].cuda() for x in g["tasks"][:t + 1]]
+            ref_keys_t = [x["keys_textual"].cuda() for x in g["tasks"][:t + 1]]
+            sel_i_ref = learner._task_id(net.extract_vector(imgs), ref_keys_i)
+            sel_t_ref = learner._task_id(net.extract_textual_vector(ds.text), ref_keys_t)
             f_i = net.visual_interface(imgs, want["sel_i"].cuda())
             f_t = net.textual_interface(ds.text, want["sel_t"].cuda())
-        assert (sel_i.cpu() == want["sel_i"]).float().mean() >= 0.9 and (sel_t.cpu() == want["sel_t"]).float().mean() >= 0.9
+        assert (sel_i_ref.cpu() == want["sel_i"]).float().mean() >= 0.9 and (sel_t_ref.cpu() == want["sel_t"]).float().mean() >= 0.9
+        own_min = 0.9 if cfg["n_tasks"] <= 2 else 0.75            # own K-Means keys: more tasks = more near-tie centres to flip
+        assert (sel_i.cpu() == want["sel_i"]).float().mean() >= own_min and (sel_t.cpu() == want["sel_t"]).float().mean() >= own_min
         assert _rel(f_i, want["img_f"]) < 1e-2 and _rel(f_t, want["txt_f"]) < 1.5e-2
         # result dict: same schema as the reference, and bit-exact w.r.t. the oracle's itm_eval on the SAME features
         assert set(res["mscoco"]) == {"i2t", "t2i"} and set(res["mscoco"]["i2t"]) == set(range(t + 1))

@@ -1,5 +1,8 @@
 """Times the CTA-pair GEMM on the vision-tower shapes (CUDA events, 30 launches after warm-up).  With LPI_GEMM_PROBE=1 the kernel skips its
-A-tile TMA loads (results are WRONG): the time difference is what the shared-memory fill of the streamed operand costs."""
+A-tile TMA loads (results are WRONG): the time difference is what the shared-memory fill of the streamed operand costs.
+The probe only exists in a library built with -DLPI_DEBUG_PROBE (never the shipped one):
+    nvcc <flags of __graft_entry__.NVCC_FLAGS> -DLPI_DEBUG_PROBE -shared lpi_b200/csrc/*.cu -o /tmp/liblpi_probe.so
+    LPI_LIB_PATH=/tmp/liblpi_probe.so LPI_GEMM_PROBE=1 python tools/gemm_probe.py"""
 import os, sys, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
