@@ -603,11 +603,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // the empty / accumulator-full barriers of BOTH CTAs; every CTA's epilogue warps drain their own TMEM lanes (their 128 rows)
 // and release the accumulator on the leader's barrier (remote arrive for the peer).
 // ================================================================================================================
-template <int MODE>
+// BN_ = cluster tile width: 256, or 192 / 128 for the GEMM shapes whose tile count would otherwise leave a mostly empty last wave
+// (N = 768 at B = 64: 54 x 3 tiles of 256 = 2.19 waves of 74 clusters; 54 x 4 tiles of 192 = 2.92)
+template <int MODE, int BN_ = 256>
 struct PairCfg {
-    static constexpr int BN = 256;
+    static constexpr int BN = BN_;
     static constexpr int A_BYTES = BM * 128;                 // one k-block of A: 128 rows x 128 B
-    static constexpr int BH_BYTES = 128 * 128;               // half B tile: 128 rows x 128 B
+    static constexpr int BH_BYTES = (BN / 2) * 128;          // half B tile: BN/2 rows x 128 B
     static constexpr int A_RESIDENT_KB = 8;                  // MODE_TOPK: up to 8 k-blocks (dim <= 512) stay resident
     static constexpr int STAGE_BYTES = (MODE == MODE_GEMM) ? A_BYTES + BH_BYTES : BH_BYTES;
     static constexpr int STAGES = (MODE == MODE_GEMM) ? 6 : 5;
@@ -625,10 +627,10 @@ struct PairCfg {
 
 enum { OP_BF16 = 0, OP_TF32 = 1, OP_F16 = 2 };      // operand type of the CTA-pair GEMM
 
-template <int MODE, int EPI, int OP>
-__global__ void __launch_bounds__(PairCfg<MODE>::THREADS, 1)
+template <int MODE, int EPI, int OP, int BN_ = 256>
+__global__ void __launch_bounds__(PairCfg<MODE, BN_>::THREADS, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs p) {
-    using C = PairCfg<MODE>;
+    using C = PairCfg<MODE, BN_>;
     constexpr bool TF32 = OP == OP_TF32;
     constexpr bool F16 = OP == OP_F16;
     constexpr int BN = C::BN;
@@ -705,7 +707,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     aphase ^= 1;
                 }
                 for (int nt = n_begin; nt < n_end; ++nt) {
-                    const int n0 = nt * BN + int(rank) * 128;       // this CTA streams its half of the B tile
+                    const int n0 = nt * BN + int(rank) * (BN / 2);  // this CTA streams its half of the B tile
                     for (int kb = 0; kb < num_k; ++kb) {
                         mbar_wait(empty_bar(stage), phase ^ 1);
 #ifdef LPI_DEBUG_PROBE
@@ -746,7 +748,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 for (int nt = n_begin; nt < n_end; ++nt) {
                     mbar_wait(tempty_bar(acc), acc_phase ^ 1);
                     tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + acc * BN;
+                    const uint32_t d_tmem = tmem_base + acc * 256;
                     for (int kb = 0; kb < num_k; ++kb) {
                         mbar_wait(full_bar(stage), phase);
                         tc_fence_after();
@@ -801,7 +803,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 if (MODE == MODE_GEMM) {
                     auto do_block = [&](int c, const uint2* pre) {
                         uint32_t r[32];
-                        const uint32_t taddr = tmem_base + uint32_t(acc * BN + c * 32) + (uint32_t(quad * 32) << 16);
+                        const uint32_t taddr = tmem_base + uint32_t(acc * 256 + c * 32) + (uint32_t(quad * 32) << 16);
                         LPI_TMEM_LD_X32(taddr, r);
                         tmem_ld_wait();
                         float4* stg = reinterpret_cast<float4*>(smem_gen + C::LIST_OFF) + (warp - 2) * 32 * 8;
@@ -819,14 +821,14 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         }
                     };
                     if (kPrefetchAux) {
-                        static_assert(NCH == 4, "the aux prefetch schedule below is written for 4 blocks per warp");
+                        static_assert(NCH >= 2 && NCH <= 4, "the aux prefetch schedule below is written for 2-4 blocks per warp");
                         const int cb = col_half * NCH;
                         do_block(cb + 0, pre0);
-                        prefetch_aux_block(p, m0 + quad * 32, n0 + (cb + 2) * 32, lane, pre0);
+                        if (NCH > 2) prefetch_aux_block(p, m0 + quad * 32, n0 + (cb + 2) * 32, lane, pre0);
                         do_block(cb + 1, pre1);
-                        prefetch_aux_block(p, m0 + quad * 32, n0 + (cb + 3) * 32, lane, pre1);
-                        do_block(cb + 2, pre0);
-                        do_block(cb + 3, pre1);
+                        if (NCH > 3) prefetch_aux_block(p, m0 + quad * 32, n0 + (cb + 3) * 32, lane, pre1);
+                        if (NCH > 2) do_block(cb + 2, pre0);
+                        if (NCH > 3) do_block(cb + 3, pre1);
                     } else {
 #pragma unroll 1
                         for (int c = col_half * NCH; c < (col_half + 1) * NCH; ++c) do_block(c, nullptr);
@@ -836,7 +838,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll 1
                     for (int c = 0; c < BN / 64; ++c) {
                         uint32_t r[64];
-                        const uint32_t taddr = tmem_base + uint32_t(acc * BN + c * 64) + (uint32_t(quad * 32) << 16);
+                        const uint32_t taddr = tmem_base + uint32_t(acc * 256 + c * 64) + (uint32_t(quad * 32) << 16);
                         LPI_TMEM_LD_X64(taddr, r);
                         tmem_ld_wait();
                         if (p.seed_mode) tmax = fmaxf(tmax, block_max<64>(r, n0 + c * 64, p.N));
@@ -932,19 +934,19 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs
     return 0;
 }
 
-template <int MODE, int EPI, int OP>
+template <int MODE, int EPI, int OP, int BN = 256>
 static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, int n_clusters, cudaStream_t st) {
-    auto kern = gemm_pair_kernel<MODE, EPI, OP>;
+    auto kern = gemm_pair_kernel<MODE, EPI, OP, BN>;
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<MODE>::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<MODE, BN>::SMEM_BYTES);
         if (e != cudaSuccess) return set_error(LPI_ERR_CUDA, "cudaFuncSetAttribute(pair): %s", cudaGetErrorString(e));
         configured = true;
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(2 * n_clusters);
-    cfg.blockDim = dim3(PairCfg<MODE>::THREADS);
-    cfg.dynamicSmemBytes = PairCfg<MODE>::SMEM_BYTES;
+    cfg.blockDim = dim3(PairCfg<MODE, BN>::THREADS);
+    cfg.dynamicSmemBytes = PairCfg<MODE, BN>::SMEM_BYTES;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -958,22 +960,32 @@ static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     return 0;
 }
 
-template <int OP>
-static int launch_pair_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, int n_clusters, cudaStream_t st) {
+template <int OP, int BN>
+static int launch_pair_epi_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, int n_clusters, cudaStream_t st) {
     constexpr bool TF32 = OP == OP_TF32;
+    constexpr int OPH = TF32 ? OP_BF16 : OP;          // the 16-bit-only epilogues are never instantiated for TF32 operands
     switch (a.epi) {
-        case EPI_BIAS_BF16: return launch_pair<MODE_GEMM, EPI_BIAS_BF16, OP>(tmA, tmB, a, n_clusters, st);
-        case EPI_BIAS_RESID_F32: return launch_pair<MODE_GEMM, EPI_BIAS_RESID_F32, OP>(tmA, tmB, a, n_clusters, st);
-        case EPI_F32: return launch_pair<MODE_GEMM, EPI_F32, OP>(tmA, tmB, a, n_clusters, st);
-        case EPI_BF16: return launch_pair<MODE_GEMM, EPI_BF16, OP>(tmA, tmB, a, n_clusters, st);
-        case EPI_BIAS_GELU_BF16: if (!TF32) return launch_pair<MODE_GEMM, EPI_BIAS_GELU_BF16, TF32 ? OP_BF16 : OP>(tmA, tmB, a, n_clusters, st); break;
-        case EPI_DGELU_BF16: if (!TF32) return launch_pair<MODE_GEMM, EPI_DGELU_BF16, TF32 ? OP_BF16 : OP>(tmA, tmB, a, n_clusters, st); break;
-        case EPI_BIAS_F32: if (!TF32) return launch_pair<MODE_GEMM, EPI_BIAS_F32, TF32 ? OP_BF16 : OP>(tmA, tmB, a, n_clusters, st); break;
-        case EPI_ACC_F32: if (!TF32) return launch_pair<MODE_GEMM, EPI_ACC_F32, TF32 ? OP_BF16 : OP>(tmA, tmB, a, n_clusters, st); break;
-        case EPI_BIAS_GELU_F32: if (TF32) return launch_pair<MODE_GEMM, EPI_BIAS_GELU_F32, OP_TF32>(tmA, tmB, a, n_clusters, st); break;
-        case EPI_DGELU_F32: if (TF32) return launch_pair<MODE_GEMM, EPI_DGELU_F32, OP_TF32>(tmA, tmB, a, n_clusters, st); break;
+        case EPI_BIAS_BF16: return launch_pair<MODE_GEMM, EPI_BIAS_BF16, OP, BN>(tmA, tmB, a, n_clusters, st);
+        case EPI_BIAS_RESID_F32: return launch_pair<MODE_GEMM, EPI_BIAS_RESID_F32, OP, BN>(tmA, tmB, a, n_clusters, st);
+        case EPI_F32: return launch_pair<MODE_GEMM, EPI_F32, OP, BN>(tmA, tmB, a, n_clusters, st);
+        case EPI_BF16: return launch_pair<MODE_GEMM, EPI_BF16, OP, BN>(tmA, tmB, a, n_clusters, st);
+        case EPI_BIAS_GELU_BF16: if (!TF32) return launch_pair<MODE_GEMM, EPI_BIAS_GELU_BF16, OPH, BN>(tmA, tmB, a, n_clusters, st); break;
+        case EPI_DGELU_BF16: if (!TF32) return launch_pair<MODE_GEMM, EPI_DGELU_BF16, OPH, BN>(tmA, tmB, a, n_clusters, st); break;
+        case EPI_BIAS_F32: if (!TF32) return launch_pair<MODE_GEMM, EPI_BIAS_F32, OPH, BN>(tmA, tmB, a, n_clusters, st); break;
+        case EPI_ACC_F32: if (!TF32) return launch_pair<MODE_GEMM, EPI_ACC_F32, OPH, BN>(tmA, tmB, a, n_clusters, st); break;
+        case EPI_BIAS_GELU_F32: if (TF32 && BN == 256) return launch_pair<MODE_GEMM, EPI_BIAS_GELU_F32, OP_TF32, 256>(tmA, tmB, a, n_clusters, st); break;
+        case EPI_DGELU_F32: if (TF32 && BN == 256) return launch_pair<MODE_GEMM, EPI_DGELU_F32, OP_TF32, 256>(tmA, tmB, a, n_clusters, st); break;
     }
-    return set_error(LPI_ERR_ARG, "epilogue %d is not available for this operand type", a.epi);
+    return set_error(LPI_ERR_ARG, "epilogue %d is not available for this operand type / tile width %d", a.epi, BN);
+}
+
+template <int OP>
+static int launch_pair_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, int n_clusters, int bn, cudaStream_t st) {
+    if (OP != OP_TF32) {                              // narrower cluster tiles exist for the 16-bit operand types only
+        if (bn == 192) return launch_pair_epi_bn<OP == OP_TF32 ? OP_BF16 : OP, 192>(tmA, tmB, a, n_clusters, st);
+        if (bn == 128) return launch_pair_epi_bn<OP == OP_TF32 ? OP_BF16 : OP, 128>(tmA, tmB, a, n_clusters, st);
+    }
+    return launch_pair_epi_bn<OP, 256>(tmA, tmB, a, n_clusters, st);
 }
 
 template <int BN>
@@ -1025,19 +1037,35 @@ static int gemm_entry(int op, const void* A, const void* B, int M, int N, int K,
     if (!out) return set_error(LPI_ERR_ARG, "gemm: null output");
     int bn = tile_n;
     const int sms = num_sms();
+    // tile_n: 0 = automatic; 128 / 256 = 1-CTA 128 x tile_n tiles; 512 (= 1256) / 1192 / 1128 = CTA-pair 256 x {256, 192, 128} cluster tiles
+    int pair_bn = 0;
     if (bn == 0) {
-        // CTA-pair 256 x 256 tiles whenever N allows: they measured at or above the 1-CTA tiles on every encoder shape
-        // (profiles/r2_gemm_microbench.txt); otherwise the narrow 1-CTA tile.
-        bn = (N % 256 == 0) ? 512 : 128;
-    }
-    const bool pair = (bn == 512);               // CTA-pair kernel: 256 x 256 tile over two SMs (cta_group::2)
-    if (bn != 128 && bn != 256 && bn != 512) return set_error(LPI_ERR_ARG, "gemm: tile_n must be 0, 128, 256 or 512 (CTA pair)");
-    if (N % (pair ? 256 : bn)) return set_error(LPI_ERR_ARG, "gemm: N=%d not a multiple of the tile width (tile_n=%d)", N, bn);
+        // CTA-pair tiles whenever N allows: they measured at or above the 1-CTA tiles on every encoder shape
+        // (profiles/r2_gemm_microbench.txt).  The cluster tile width is the one that wastes least of the last wave: full waves of 74
+        // clusters x a per-tile efficiency (a narrower tile streams more operand bytes per FLOP).
+        const long mp = ((M + BM - 1) / BM + 1) / 2;
+        double best = 0.0;
+        const int cand[3] = {256, 192, 128};
+        const double weight[3] = {1.0, 0.96, 0.88};
+        for (int i = 0; i < 3; ++i) {
+            if (N % cand[i] || (tf32 && cand[i] != 256)) continue;
+            const long tiles = mp * (N / cand[i]), cl = sms / 2;
+            const double eff = double(tiles) / double(((tiles + cl - 1) / cl) * cl) * weight[i];
+            if (eff > best + 1e-9) { best = eff; pair_bn = cand[i]; }
+        }
+        if (!pair_bn) bn = 128;
+    } else if (bn == 512 || bn == 1256) pair_bn = 256;
+    else if (bn == 1192) pair_bn = 192;
+    else if (bn == 1128) pair_bn = 128;
+    else if (bn != 128 && bn != 256) return set_error(LPI_ERR_ARG, "gemm: tile_n must be 0, 128, 256 (1-CTA) or 512 / 1192 / 1128 (CTA pair)");
+    const bool pair = pair_bn != 0;
+    if (pair && tf32 && pair_bn != 256) return set_error(LPI_ERR_ARG, "gemm_tf32: only the 256-wide CTA-pair tile is built");
+    if (N % (pair ? pair_bn : bn)) return set_error(LPI_ERR_ARG, "gemm: N=%d not a multiple of the tile width (tile_n=%d)", N, tile_n);
     CUtensorMap tmA, tmB;
     const CUtensorMapDataType dt = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : (op == OP_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
     const int eb = tf32 ? 4 : 2;
     if (int rc = make_tmap_2d(&tmA, A, dt, eb, M, K, K, BM, bke)) return rc;
-    if (int rc = make_tmap_2d(&tmB, B, dt, eb, N, K, K, pair ? 128 : bn, bke)) return rc;
+    if (int rc = make_tmap_2d(&tmB, B, dt, eb, N, K, K, pair ? pair_bn / 2 : bn, bke)) return rc;
     GemmArgs a{};
     a.M = M; a.N = N; a.K = K; a.epi = epi; a.ldo = ldo;
     {
@@ -1074,12 +1102,13 @@ static int gemm_entry(int op, const void* A, const void* B, int M, int N, int K,
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (pair) {
-        const long ctiles = long(((M + BM - 1) / BM + 1) / 2) * (N / 256);
+        const long ctiles = long(((M + BM - 1) / BM + 1) / 2) * (N / pair_bn);
         const int n_clusters = int(ctiles < sms / 2 ? ctiles : sms / 2);
-        return tf32 ? launch_pair_epi<OP_TF32>(tmA, tmB, a, n_clusters, st)
-                    : (op == OP_F16 ? launch_pair_epi<OP_F16>(tmA, tmB, a, n_clusters, st) : launch_pair_epi<OP_BF16>(tmA, tmB, a, n_clusters, st));
+        return tf32 ? launch_pair_epi<OP_TF32>(tmA, tmB, a, n_clusters, pair_bn, st)
+                    : (op == OP_F16 ? launch_pair_epi<OP_F16>(tmA, tmB, a, n_clusters, pair_bn, st)
+                                    : launch_pair_epi<OP_BF16>(tmA, tmB, a, n_clusters, pair_bn, st));
     }
-    if (op == OP_F16) return set_error(LPI_ERR_UNSUPPORTED, "gemm_f16: N=%d must be a multiple of 256 (CTA-pair tiles only)", N);
+    if (op == OP_F16) return set_error(LPI_ERR_UNSUPPORTED, "gemm_f16: CTA-pair tiles only (tile_n 0 / 512 / 1192 / 1128)");
     const long tiles = long((M + BM - 1) / BM) * (N / bn);
     const int grid = int(tiles < sms ? tiles : sms);
     if (tf32) return bn == 256 ? launch_epi_tf32<256>(tmA, tmB, a, grid, st) : launch_epi_tf32<128>(tmA, tmB, a, grid, st);
@@ -1102,7 +1131,7 @@ extern "C" int lpi_gemm_f16(const void* A, const void* B, int M, int N, int K, i
                             void* out2, const void* aux, int ldo, int tile_n, void* stream) {
     if (epi == EPI_BIAS_GELU_F32 || epi == EPI_DGELU_F32)
         return set_error(LPI_ERR_ARG, "gemm_f16: epilogue %d is only available for TF32 operands", epi);
-    if (tile_n != 0 && tile_n != 512) return set_error(LPI_ERR_ARG, "gemm_f16: only the CTA-pair tile (tile_n 0 or 512) is built");
+    if (tile_n == 128 || tile_n == 256) return set_error(LPI_ERR_ARG, "gemm_f16: only the CTA-pair tiles (tile_n 0 / 512 / 1192 / 1128) are built");
     return gemm_entry(OP_F16, A, B, M, N, K, epi, bias, resid, out, out2, aux, ldo, tile_n, stream);
 }
 

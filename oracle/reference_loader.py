@@ -4,6 +4,10 @@ golden vectors can be generated (tests/golden/make_golden.py).
 
 Nothing under `lpi_b200/` may import this module.  `/root/reference` only exists in the
 build container, never on the GPU box: callers must check `reference_available()`.
+`__graft_entry__.build()` stages an UNMODIFIED copy of the reference's `retrieval/` package under
+`baseline/_ref/retrieval` (git-ignored, so never part of the history, but shipped to the GPU box):
+that copy is what `bench.py`'s reference legs time on the box's host cores and -- through stock
+torch -- on the B200 itself (`cuda=True`, the "GPU eager" kernel to beat).
 
 The reference has no FFI/test harness of its own; to import it on a CPU-only box we need
 (SURVEY.md section 8(c)):
@@ -24,7 +28,18 @@ import sys
 import tempfile
 import types
 
-REFERENCE_ROOT = os.environ.get("LPI_REFERENCE_ROOT", "/root/reference/retrieval")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+STAGED_ROOT = os.path.join(_REPO, "baseline", "_ref", "retrieval")
+
+
+def _find_root() -> str:
+    for c in (os.environ.get("LPI_REFERENCE_ROOT"), "/root/reference/retrieval", STAGED_ROOT):
+        if c and os.path.isfile(os.path.join(c, "models", "slinet.py")):
+            return c
+    return "/root/reference/retrieval"
+
+
+REFERENCE_ROOT = _find_root()
 
 _loaded = {}
 
@@ -95,9 +110,13 @@ def in_reference_cwd():
         os.chdir(old)
 
 
-def load_reference():
-    """Import the reference modules (once) and return a namespace of the ones on the hot path."""
+def load_reference(cuda: bool = False):
+    """Import the reference modules (once) and return a namespace of the ones on the hot path.
+    cuda=False (default): CPU oracle -- `.cuda()` and the device queries are patched out.  cuda=True (bench.py's GPU-eager leg on the
+    B200 box): nothing is patched, the reference runs through stock torch on the current CUDA device.  One mode per process."""
     if "ns" in _loaded:
+        if _loaded.get("cuda") != cuda:
+            raise RuntimeError("the reference was already loaded in the other device mode in this process")
         return _loaded["ns"]
     if not reference_available():
         raise RuntimeError(f"reference not found under {REFERENCE_ROOT}")
@@ -106,10 +125,12 @@ def load_reference():
     _install_stubs()
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
-    # CPU-only patches (prompt_learner.py:122,132,146-148)
-    torch.Tensor.cuda = lambda self, *a, **k: self
-    torch.cuda.current_device = lambda: 0
-    torch.cuda.device_count = lambda: 1
+    if not cuda:
+        # CPU-only patches (prompt_learner.py:122,132,146-148)
+        torch.Tensor.cuda = lambda self, *a, **k: self
+        torch.cuda.current_device = lambda: 0
+        torch.cuda.device_count = lambda: 1
+    _loaded["cuda"] = cuda
     with in_reference_cwd():
         import models.slinet as slinet
         import models.clip.model as clip_model

@@ -1,5 +1,6 @@
 """CPU checks of the bench.py contract that do not need a GPU: the reference arm (`--impl reference`) runs the oracle port of the
-reference's procedure on the host cores and prints ONE JSON line with the agreed keys; under torchrun only rank 0 prints."""
+reference's procedure (the real itm_eval for small galleries) on the host cores and prints ONE JSON line with the agreed keys; under
+torchrun only rank 0 prints."""
 import json
 import os
 import subprocess
@@ -27,7 +28,11 @@ def test_reference_arm_prints_one_contract_line():
     assert d["steps"] == 2 and d["warmup"] == 1 and d["n_gpus"] == 1 and d["value"] > 0 and d["ms_per_step"] > 0
     assert d["config"]["workload"].startswith("large-gallery Recall@K sweep") and d["config"]["gallery"] == 3000
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] == (os.cpu_count() or 1) and cb["value"] == d["value"] and "queries per step" in cb["sample"]
+    # small galleries run the REAL reference's itm_eval when its tree is there (build container, or the baseline/_ref copy on the box)
+    sys.path.insert(0, ROOT)
+    from oracle import reference_loader as RL
+    assert cb["kind"] == ("reference" if RL.reference_available() else "port")
+    assert cb["cores"] == (os.cpu_count() or 1) and cb["value"] == d["value"] and "queries per step" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 

@@ -51,9 +51,9 @@ def _case(M, N, K, epi, tile_n, seed=0, half=torch.bfloat16):
 
 @pytest.mark.parametrize("M,N,K", [(100, 128, 64), (300, 512, 512), (4928, 1536, 512), (13632, 2304, 768),
                                    (13632, 768, 3072), (1, 128, 64)])
-@pytest.mark.parametrize("tile_n", [0, 128, 256, 512])
+@pytest.mark.parametrize("tile_n", [0, 128, 256, 512, 1192, 1128])
 def test_gemm_shapes(M, N, K, tile_n):
-    if tile_n and N % min(tile_n, 256):
+    if tile_n and N % {128: 128, 256: 256, 512: 256, 1192: 192, 1128: 128}[tile_n]:
         pytest.skip("N not a multiple of the tile")
     _case(M, N, K, ops.EPI_F32, tile_n)
 
@@ -67,6 +67,16 @@ def test_gemm_epilogues(epi):
 
 
 @pytest.mark.parametrize("epi", range(8))
+@pytest.mark.parametrize("tile_n", [1192, 1128])
+def test_gemm_narrow_pair_tiles(epi, tile_n):
+    """CTA-pair kernel with 256 x 192 / 256 x 128 cluster tiles (picked automatically when 256-wide tiles would leave the last wave
+    mostly empty, e.g. N = 768 at B = 64): every epilogue, ragged M, both 16-bit operand types."""
+    _case(1000, 768, 768, epi, tile_n, seed=7)
+    _case(13632, 768, 3072, epi, tile_n, seed=8)
+    _case(2496, 1536, 512, epi, tile_n, seed=9, half=torch.float16)
+
+
+@pytest.mark.parametrize("epi", range(8))
 def test_gemm_f16_epilogues(epi):
     """fp16 operands (text tower): same epilogues, every 16-bit tensor is fp16, tolerance = fp16 output rounding."""
     _case(1000, 768, 768, epi, 0, seed=4, half=torch.float16)
@@ -75,12 +85,16 @@ def test_gemm_f16_epilogues(epi):
 
 
 def test_gemm_f16_rejects_narrow_n():
+    """fp16 operands run on the CTA-pair kernel only (cluster tiles of 128 / 192 / 256 columns); the 1-CTA tiles are bf16 / TF32."""
     from lpi_b200._lib import LpiError
 
     a = torch.zeros(64, 64, device="cuda", dtype=torch.float16)
-    w = torch.zeros(128, 64, device="cuda", dtype=torch.float16)
+    w = torch.zeros(64, 64, device="cuda", dtype=torch.float16)
     with pytest.raises(LpiError):
         ops.gemm(a, w, ops.EPI_F32)
+    w = torch.zeros(128, 64, device="cuda", dtype=torch.float16)
+    with pytest.raises(LpiError):
+        ops.gemm(a, w, ops.EPI_F32, tile_n=128)
 
 
 def test_gemm_rejects_bad_shapes():
