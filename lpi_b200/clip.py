@@ -205,7 +205,7 @@ def load_clip_to_cpu(args) -> CLIP:
     (a state_dict or a path to one) or, failing that, a random-init ViT-B/16 (there is no network on the box)."""
     src = args.get("clip_state_dict") if isinstance(args, dict) else None
     if isinstance(src, str):
-        src = torch.load(src, map_location="cpu")
+        src = torch.load(src, map_location="cpu", weights_only=True)      # a state_dict: tensors only
     if src is not None:
         return build_model(src)
     return CLIP(512, 224, 12, 768, 16, 77, 49408, 512, 8, 12).eval()

@@ -38,10 +38,10 @@ def gather_features(image_features, text_features, local_loss=False, gather_with
     if world_size == 1:
         return image_features, text_features
     if gather_with_grad:
-        import torch.distributed.nn
+        import torch.distributed.nn as dist_nn       # (a bare `import torch.distributed.nn` here would shadow the module-level `torch`)
 
-        all_image_features = torch.cat(torch.distributed.nn.all_gather(image_features), dim=0)
-        all_text_features = torch.cat(torch.distributed.nn.all_gather(text_features), dim=0)
+        all_image_features = torch.cat(dist_nn.all_gather(image_features), dim=0)
+        all_text_features = torch.cat(dist_nn.all_gather(text_features), dim=0)
     else:
         gi = [torch.zeros_like(image_features) for _ in range(world_size)]
         gt = [torch.zeros_like(text_features) for _ in range(world_size)]
@@ -53,6 +53,35 @@ def gather_features(image_features, text_features, local_loss=False, gather_with
         all_image_features = torch.cat(gi, dim=0)
         all_text_features = torch.cat(gt, dim=0)
     return all_image_features, all_text_features
+
+
+def gather_rows(t: torch.Tensor, group) -> torch.Tensor:
+    """All ranks' rows of a [n_r, d] tensor concatenated rank-major on every rank; n_r may differ per rank (ragged last shard of a
+    loader).  Backend-agnostic (NCCL on the box, gloo in the CPU tests)."""
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    if world == 1:
+        return t
+    n = torch.tensor([t.shape[0]], device=t.device, dtype=torch.int64)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    sizes = [int(x) for x in sizes]
+    m = max(sizes)
+    pad = torch.zeros(m, *t.shape[1:], device=t.device, dtype=t.dtype)
+    pad[: t.shape[0]] = t
+    out = torch.empty(world * m, *t.shape[1:], device=t.device, dtype=t.dtype)
+    dist.all_gather_into_tensor(out, pad.contiguous(), group=group)
+    return torch.cat([out[r * m: r * m + sizes[r]] for r in range(world)], dim=0)
+
+
+def is_main_rank(group) -> bool:
+    """True on the one rank that writes files (checkpoints, ./res/*.json) in a data-parallel run."""
+    if group is None:
+        return True
+    import torch.distributed as dist
+
+    return dist.get_rank(group) == 0
 
 
 class AverageMeter(object):
@@ -198,14 +227,24 @@ class SPrompts(object):
                 "results": {int(t): r for t, r in (results or {}).items()}}
 
     def save_checkpoint(self, path: str, results: Optional[dict] = None) -> str:
-        tmp = path + ".tmp"
-        torch.save(self.checkpoint_state(results), tmp)
-        os.replace(tmp, path)                              # a crash mid-write never leaves a truncated checkpoint behind
+        """Data-parallel runs: every rank holds the same state (replicated prompts, gathered task keys), rank 0 alone writes, everybody
+        leaves together -- concurrent ranks would otherwise race on the shared `.tmp` file."""
+        if is_main_rank(self.group):
+            tmp = path + ".tmp"
+            torch.save(self.checkpoint_state(results), tmp)
+            os.replace(tmp, path)                          # a crash mid-write never leaves a truncated checkpoint behind
+        self._barrier()
         return path
+
+    def _barrier(self):
+        if self.group is not None:
+            import torch.distributed as dist
+
+            dist.barrier(group=self.group)
 
     def load_checkpoint(self, path: str) -> dict:
         """Restores prompts / contexts, task keys and counters; returns the results recorded so far ({task: result dict})."""
-        st = torch.load(path, map_location="cpu", weights_only=False)
+        st = torch.load(path, map_location="cpu", weights_only=True)    # v1 holds tensors, ints, lists and dicts of floats only
         if st.get("format") != "lpi_b200.checkpoint.v1":
             raise LpiError(f"{path} is not an lpi_b200 checkpoint")
         own = self._network.state_dict()
@@ -226,8 +265,10 @@ class SPrompts(object):
         return {int(t): r for t, r in st["results"].items()}
 
     def save_dict(self, dictionary, file_path):
-        with open(file_path, "w") as f:
-            json.dump(dictionary, f)
+        if is_main_rank(self.group):
+            with open(file_path, "w") as f:
+                json.dump(dictionary, f)
+        self._barrier()
 
     def _train(self, train_loader, test_loader):
         self._task_consts.clear()                              # per-task caches of the fused step (earlier prompts may have been reloaded)
@@ -361,12 +402,26 @@ class SPrompts(object):
                 tf.append(self._network.extract_textual_vector(captions))
         vf = torch.cat(vf, 0)
         tf = torch.cat(tf, 0)
+        if self.group is not None:
+            # data-parallel: each rank saw its own shard of the task's train set; the keys must come from ALL of it and be identical on
+            # every rank (they drive the task-id selection at evaluation time), so the features are gathered (rank-major) ...
+            vf, tf = gather_rows(vf.contiguous(), self.group), gather_rows(tf.contiguous(), self.group)
         vf = ops.l2_normalize(vf.contiguous()).cpu().numpy()       # the reference re-normalises (sprompt.py:387-390)
         tf = ops.l2_normalize(tf.contiguous()).cpu().numpy()
         vc = KMeans(n_clusters=5, random_state=0).fit(vf)
         tc = KMeans(n_clusters=5, random_state=0).fit(tf)
-        self.all_keys.append(torch.tensor(vc.cluster_centers_).to(self._device))
-        self.textual_all_keys.append(torch.tensor(tc.cluster_centers_).to(self._device))
+        keys_v = torch.tensor(vc.cluster_centers_).to(self._device)
+        keys_t = torch.tensor(tc.cluster_centers_).to(self._device)
+        if self.group is not None:
+            import torch.distributed as dist
+
+            # ... and rank 0's centres are the ones everybody keeps (host K-Means is deterministic for identical inputs, but a different
+            # BLAS / thread count on one rank must not be able to split the ranks)
+            src = dist.get_global_rank(self.group, 0)
+            dist.broadcast(keys_v, src=src, group=self.group)
+            dist.broadcast(keys_t, src=src, group=self.group)
+        self.all_keys.append(keys_v)
+        self.textual_all_keys.append(keys_t)
 
     # ------------------------------------------------------------------ evaluation
     @torch.no_grad()
