@@ -598,8 +598,11 @@ def train_leg(dev, world, rank, group, steps, warmup, peaks, args, batch_per_gpu
     fac = {k: v.to(dev) for k, v in S.make_prompt_factors(0).items()}
     fac0 = {k: v.clone() for k, v in fac.items()}
     opt = lpi_step.PromptSGD(fac, 0.05)
+    from lpi_b200 import tokenizer as T
+
     images_host = S.make_images(batch_per_gpu, rank).pin_memory()
-    tokens_host = S.make_tokens(batch_per_gpu, rank)
+    # the same captions the reference legs get, through PromptLearner's template "X X ... X <caption>." (prompt_learner.py:128-132)
+    tokens_host = T.tokenize([" ".join(["X"] * 16) + " " + c + "." for c in S.make_captions(batch_per_gpu, rank)])
     text_len = int(tokens_host.argmax(dim=-1).max()) + 1      # host-side, as the tokenizer provides it: positions after the last EOT are dead
     if world > 1:                                             # one bound for all ranks (a longer bound is still exact)
         tl = torch.tensor([text_len], device=dev)
@@ -614,7 +617,7 @@ def train_leg(dev, world, rank, group, steps, warmup, peaks, args, batch_per_gpu
         r_dp = lpi_step.train_step(vision, text, fac0, images, tokens, 1 / 0.07, group=group, text_len=text_len)
         if rank == 0:
             gi = torch.cat([S.make_images(batch_per_gpu, r) for r in range(world)]).to(dev)
-            gtk = torch.cat([S.make_tokens(batch_per_gpu, r) for r in range(world)]).to(dev)
+            gtk = torch.cat([T.tokenize([" ".join(["X"] * 16) + " " + c + "." for c in S.make_captions(batch_per_gpu, r)]) for r in range(world)]).to(dev)
             r_1 = lpi_step.train_step(vision, text, fac0, gi, gtk, 1 / 0.07, text_len=text_len)
             rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm())
             parity = {"global_batch": batch_per_gpu * world,
@@ -742,9 +745,7 @@ def _reference_train_setup(batch, cuda, dtype=None):
             m.load_state_dict(sd)
             if dtype == "fp16":
                 ns.clip_model.convert_weights(m)            # what build_model does for every GPU run (model.py:394-415, 522)
-            else:
-                m = m.to(torch.bfloat16)
-            return m.cuda()
+            return m.cuda()                                 # bf16: fp32 weights under torch.autocast (the reference's LayerNorm subclass rejects bf16 weights)
         ns.slinet.load_clip_to_cpu = make_clip
         with RL.in_reference_cwd():
             args = RL.reference_args()
@@ -764,12 +765,15 @@ def _reference_train_setup(batch, cuda, dtype=None):
     if cuda:
         images = images.cuda()
 
+    import contextlib
+
     def step(n=batch):
         # the loop body of train_function, sprompt.py:300-311
-        img_f, txt_f, vp, tp = net(images[:n], captions[:n])
-        with RL.in_reference_cwd():
-            out = net.cal_loss(img_f, txt_f, vp, tp)
-        loss = sum(l for l in out["loss"].values())
+        with (torch.autocast("cuda", dtype=torch.bfloat16) if (cuda and dtype == "bf16") else contextlib.nullcontext()):
+            img_f, txt_f, vp, tp = net(images[:n], captions[:n])
+            with RL.in_reference_cwd():
+                out = net.cal_loss(img_f, txt_f, vp, tp)
+            loss = sum(l for l in out["loss"].values())
         opt.zero_grad()
         loss.backward()
         opt.step()
@@ -828,7 +832,7 @@ def main():
     ap.add_argument("--gallery", type=int, default=5_000_000)
     ap.add_argument("--queries", type=int, default=25_000)
     ap.add_argument("--e2e-chunks", type=int, default=8, help="host->device pipeline depth of the e2e leg (gallery shard copied in this many pieces)")
-    ap.add_argument("--e2e-streams", type=int, default=2, help="copy streams the e2e leg spreads its host->device chunks over")
+    ap.add_argument("--e2e-streams", type=int, default=1, help="copy streams the e2e leg spreads its host->device chunks over")
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs: no cpu_baseline / reference legs")
     ap.add_argument("--skip-train", action="store_true", help="skip the secondary train pairs/s leg")
     ap.add_argument("--skip-sweep", action="store_true", help="skip the smaller-gallery / Flickr-shaped informational leg")

@@ -89,6 +89,13 @@ int lpi_sim_topk_seed_bf16(const void* Q, const void* G, int n_queries, int n_ro
 /* k-way merge of n_parts partial lists (chunks and/or all-gathered shards) -> [n_queries, k]. */
 int lpi_topk_merge(const float* part_scores, const int* part_idx, int n_parts, int n_queries, int k,
                    float* out_scores, int* out_idx, void* stream);
+/* The whole tail of a gallery-sharded search step in one launch: k-way merge of chunk / rank lists + Recall@K bookkeeping
+ * (sprompt.py:559-619).  Parts may be grouped (one group per rank of an all-gathered exchange buffer): part p is read at
+ * (p / parts_per_group) * group_stride + (p % parts_per_group) * n_queries * k elements from part_scores / part_idx.
+ * counts[n_tasks,4] (zeroed here) = #{rank<1}, #{rank<5}, #{rank<10}, n per task; rank_out[n_queries] optional (k = not in the list). */
+int lpi_topk_merge_recall(const float* part_scores, const int* part_idx, int n_parts, int parts_per_group, long long group_stride,
+                          int n_queries, int k, float* out_scores, int* out_idx, const int* gt_ptr, const int* gt_idx,
+                          const int* task_of_query, int n_tasks, int* counts, int* rank_out, void* stream);
 /* Top-k of each row of a dense fp32 score matrix (drop-in `itm_eval(scores_i2t, scores_t2i, ...)`,
  * methods/sprompt.py:550-567,594-599); ties -> lowest index. */
 int lpi_topk_rows_f32(const float* scores, int n_rows, int n_cols, long long ld, int k, float* out_scores,

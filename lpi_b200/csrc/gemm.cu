@@ -29,6 +29,15 @@ constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BM * BK * 2;
 constexpr int GEMM_THREADS = 192;
 constexpr int TOPK_MAX = 16;
+#ifndef LPI_RASTER_N
+#define LPI_RASTER_N 1       // pair GEMM tile order: 1 = N fastest (A block fetched once, hit in L2 by its other N tiles), 0 = M fastest (A/B builds)
+#endif
+#ifndef LPI_H2_ACT
+#define LPI_H2_ACT 1         // fp16 towers: (d)QuickGELU on packed halves (0 = fp32 arithmetic as in the bf16 tower; A/B builds)
+#endif
+#ifndef LPI_EPI_DIRECT
+#define LPI_EPI_DIRECT 0     // pair GEMM epilogue: 1 = accumulator rows straight to global memory with 256-bit accesses (no smem staging)
+#endif
 #ifndef LPI_EPI16
 #define LPI_EPI16 1          // 16-bit staging of 16-bit outputs in the pair GEMM epilogue (0 = the fp32 transpose for every epilogue)
 #endif
@@ -144,6 +153,30 @@ __device__ __forceinline__ float sigmoid_fast(float x) {
     asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * x));
     return fmaf(0.5f, t, 0.5f);
 }
+// fp16 towers: the same two functions on PACKED halves -- the 16-bit epilogues are instruction-bound (the dQuickGELU epilogue executed 4x the
+// instructions of the plain one and held the tensor pipe at 50 %, profiles/r2_gemm_vs_cublas.md), and both their input (the fp16
+// pre-activation, stored for the backward either way) and their output are fp16, so fp16 arithmetic costs ~1.5 ulp(fp16) on top of the
+// output rounding: ONE MUFU op and 3-5 HFMA2-class instructions per TWO elements.
+__device__ __forceinline__ uint32_t h2_sigmoid_1702(uint32_t z2) {          // sigmoid(1.702 z) = 0.5 tanh(0.851 z) + 0.5
+    const __half2 z = *reinterpret_cast<const __half2*>(&z2);
+    const __half2 a = __hmul2(z, __float2half2_rn(0.851f));
+    uint32_t t;
+    asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(*reinterpret_cast<const uint32_t*>(&a)));
+    const __half2 s = __hfma2(*reinterpret_cast<const __half2*>(&t), __float2half2_rn(0.5f), __float2half2_rn(0.5f));
+    return *reinterpret_cast<const uint32_t*>(&s);
+}
+__device__ __forceinline__ uint32_t h2_quick_gelu(uint32_t z2) {
+    const uint32_t s2 = h2_sigmoid_1702(z2);
+    const __half2 r = __hmul2(*reinterpret_cast<const __half2*>(&z2), *reinterpret_cast<const __half2*>(&s2));
+    return *reinterpret_cast<const uint32_t*>(&r);
+}
+__device__ __forceinline__ float2 h2_quick_gelu_grad(uint32_t z2) {          // s + 1.702 z s (1 - s)
+    const uint32_t s2 = h2_sigmoid_1702(z2);
+    const __half2 s = *reinterpret_cast<const __half2*>(&s2);
+    const __half2 u = __hmul2(*reinterpret_cast<const __half2*>(&z2), __float2half2_rn(1.702f));
+    const __half2 q = __hfma2(__hneg2(s), s, s);                              // s (1 - s)
+    return __half22float2(__hfma2(u, q, s));
+}
 template <bool PRECISE = false>
 __device__ __forceinline__ float quick_gelu(float z) { return z * sigmoid_fast<PRECISE>(1.702f * z); }
 template <bool PRECISE = false>
@@ -179,7 +212,7 @@ __device__ __forceinline__ float2 unpack_h2(uint32_t w) {
 
 template <int EPI, bool F16 = false>
 __device__ __forceinline__ void epilogue_block(const GemmArgs& p, const float4* __restrict__ st, int row0, int col0, int lane,
-                                               const uint2* pre_aux = nullptr) {
+                                               const uint2* pre_aux = nullptr, const float4* pre_resid = nullptr) {
     constexpr bool kBias = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_F32 ||
                             EPI == EPI_BIAS_GELU_F32);
     constexpr bool kF32Out = (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_F32 || EPI == EPI_ACC_F32 || EPI == EPI_BIAS_F32 ||
@@ -202,8 +235,10 @@ __device__ __forceinline__ void epilogue_block(const GemmArgs& p, const float4* 
             const float* src = (EPI == EPI_BIAS_RESID_F32) ? p.resid : (EPI == EPI_ACC_F32 ? p.out_f32 : p.aux_f32);
             float4 e[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-                e[i] = (i * 4 + rsub < rows) ? *reinterpret_cast<const float4*>(src + base + size_t(i * 4) * p.ldo) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = 0; i < 8; ++i) {
+                if (EPI == EPI_BIAS_RESID_F32 && pre_resid) e[i] = pre_resid[i];      // prefetched by the caller (see prefetch_resid_block)
+                else e[i] = (i * 4 + rsub < rows) ? *reinterpret_cast<const float4*>(src + base + size_t(i * 4) * p.ldo) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 if (EPI == EPI_DGELU_F32) {
@@ -236,6 +271,11 @@ __device__ __forceinline__ void epilogue_block(const GemmArgs& p, const float4* 
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
+                if (LPI_H2_ACT && F16 && !p.precise_act) {                  // packed-half derivative (see h2_quick_gelu_grad)
+                    const float2 d0 = h2_quick_gelu_grad(e[i].x), d1 = h2_quick_gelu_grad(e[i].y);
+                    v[i].x *= d0.x; v[i].y *= d0.y; v[i].z *= d1.x; v[i].w *= d1.y;
+                    continue;
+                }
                 const float2 z0 = unpack_h2<F16>(e[i].x);
                 const float2 z1 = unpack_h2<F16>(e[i].y);
                 if (F16 && p.precise_act) {
@@ -281,7 +321,9 @@ __device__ __forceinline__ void epilogue_block16(const GemmArgs& p, const uint32
         v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b4.w;
     }
     const int sw = (lane >> 1) & 3;
-    auto stage_and_store = [&](__nv_bfloat16* dst) {
+    // `streaming`: the saved pre-activation is read again a whole forward and half a backward later -- it goes out with an evict-first
+    // hint so that it does not push the activation the next GEMM is about to read out of the 126 MB L2
+    auto stage_and_store = [&](__nv_bfloat16* dst, bool streaming = false) {
 #pragma unroll
         for (int q = 0; q < 4; ++q)
             st[lane * 4 + (q ^ sw)] = make_uint4(pack_h2<F16>(v[8 * q], v[8 * q + 1]), pack_h2<F16>(v[8 * q + 2], v[8 * q + 3]),
@@ -291,12 +333,41 @@ __device__ __forceinline__ void epilogue_block16(const GemmArgs& p, const uint32
         for (int it = 0; it < 4; ++it) {
             const int rr = it * 8 + (lane >> 2), q = lane & 3;
             const uint4 w = st[rr * 4 + (q ^ ((rr >> 1) & 3))];
-            if (rr < rows) *reinterpret_cast<uint4*>(dst + size_t(row0 + rr) * p.ldo + col0 + q * 8) = w;
+            if (rr < rows) {
+                uint4* g = reinterpret_cast<uint4*>(dst + size_t(row0 + rr) * p.ldo + col0 + q * 8);
+                if (streaming) __stcs(g, w); else *g = w;
+            }
         }
         __syncwarp();
     };
+    if (LPI_H2_ACT && EPI == EPI_BIAS_GELU_BF16 && F16 && !p.precise_act) {
+        // fp16 tower: pack the pre-activation once, store it, then the activation on the packed halves
+        uint32_t w[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) w[j] = pack_h2<true>(v[2 * j], v[2 * j + 1]);
+        auto stage_words = [&](__nv_bfloat16* dst, bool streaming = false) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) st[lane * 4 + (q ^ sw)] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int rr = it * 8 + (lane >> 2), q = lane & 3;
+                const uint4 x = st[rr * 4 + (q ^ ((rr >> 1) & 3))];
+                if (rr < rows) {
+                    uint4* g = reinterpret_cast<uint4*>(dst + size_t(row0 + rr) * p.ldo + col0 + q * 8);
+                    if (streaming) __stcs(g, x); else *g = x;
+                }
+            }
+            __syncwarp();
+        };
+        if (p.out2_bf16) stage_words(p.out2_bf16, true);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) w[j] = h2_quick_gelu(w[j]);
+        stage_words(p.out_bf16);
+        return;
+    }
     if (EPI == EPI_BIAS_GELU_BF16) {
-        if (p.out2_bf16) stage_and_store(p.out2_bf16);          // pre-activation, kept for the backward
+        if (p.out2_bf16) stage_and_store(p.out2_bf16, true);    // pre-activation, kept for the backward
         if (F16 && p.precise_act) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = quick_gelu<true>(v[j]);
@@ -318,7 +389,131 @@ __device__ __forceinline__ void prefetch_aux_block(const GemmArgs& p, int row0, 
     const size_t base = size_t(row0 + rsub) * p.ldo + col0 + c * 4;
 #pragma unroll
     for (int i = 0; i < 8; ++i)
-        e[i] = (i * 4 + rsub < rows) ? __ldg(reinterpret_cast<const uint2*>(p.aux_bf16 + base + size_t(i * 4) * p.ldo)) : make_uint2(0u, 0u);
+        e[i] = (i * 4 + rsub < rows) ? __ldcs(reinterpret_cast<const uint2*>(p.aux_bf16 + base + size_t(i * 4) * p.ldo)) : make_uint2(0u, 0u);   // read once: evict-first
+}
+
+// Same idea for the fp32 residual of EPI_BIAS_RESID_F32 (out-proj / c_proj forward): the residual stream was written one or two kernels
+// earlier (L2 at best), and loading it inside epilogue_block exposed that latency once per 32-column block.  (The residual never aliases
+// a row another CTA writes, and this thread's own store of a block comes after its load of the same block, so in-place use stays legal.)
+__device__ __forceinline__ void prefetch_resid_block(const GemmArgs& p, int row0, int col0, int lane, float4 (&e)[8]) {
+    const int rows = min(32, p.M - row0);
+    const int rsub = lane >> 3, c = lane & 7;
+    const size_t base = size_t(row0 + rsub) * p.ldo + col0 + c * 4;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+        e[i] = (i * 4 + rsub < rows) ? *reinterpret_cast<const float4*>(p.resid + base + size_t(i * 4) * p.ldo) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// ------------------------------------------------------------------------------------------------ direct epilogue (LPI_EPI_DIRECT)
+// The smem-staged epilogues above compete with the MMA main loop for shared-memory bandwidth: a streaming 256 x 256 CTA-pair tile
+// already fills and reads ~128 B/clk, and with the epilogue removed the K = 768 GEMMs run at 1.36-1.54 PFLOP/s instead of 0.89-1.18
+// (profiles/r2_gemm_vs_cublas.md).  sm_100 has 256-bit global accesses: in the accumulator layout (thread = row) a thread's 32 columns are
+// 64 contiguous bytes (16-bit) or 128 (fp32), i.e. 2 or 4 full 32-byte sectors, so rows can go to and come from global memory directly
+// -- no staging, no __syncwarp, every sector written whole.
+__device__ __forceinline__ void ldg256(const void* ptr, uint32_t* a) {
+    asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]) : "l"(ptr));
+}
+__device__ __forceinline__ void stg256(void* ptr, const uint32_t* a) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"l"(ptr), "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(a[4]), "r"(a[5]), "r"(a[6]), "r"(a[7]) : "memory");
+}
+// saved pre-activation (16-bit, EPI_DGELU_BF16) / fp32 residual (EPI_BIAS_RESID_F32) of one row x 32 columns, issued ahead of use
+__device__ __forceinline__ void prefetch_aux_direct(const GemmArgs& p, int row, int col0, bool valid, uint32_t (&e)[16]) {
+    if (valid) {
+        const __nv_bfloat16* src = p.aux_bf16 + size_t(row) * p.ldo + col0;
+        ldg256(src, e);
+        ldg256(src + 16, e + 8);
+    }
+}
+__device__ __forceinline__ void prefetch_resid_direct(const GemmArgs& p, int row, int col0, bool valid, uint32_t (&e)[32]) {
+    if (valid) {
+        const float* src = p.resid + size_t(row) * p.ldo + col0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) ldg256(src + 8 * j, e + 8 * j);
+    }
+}
+
+template <int EPI, bool F16>
+__device__ __forceinline__ void epilogue_direct(const GemmArgs& p, const uint32_t (&r)[32], int row, int col0, bool valid, const uint32_t* pre) {
+    constexpr bool kBias = (EPI == EPI_BIAS_BF16 || EPI == EPI_BIAS_GELU_BF16 || EPI == EPI_BIAS_RESID_F32 || EPI == EPI_BIAS_F32 ||
+                            EPI == EPI_BIAS_GELU_F32);
+    constexpr bool kF32Out = (EPI == EPI_BIAS_RESID_F32 || EPI == EPI_F32 || EPI == EPI_ACC_F32 || EPI == EPI_BIAS_F32 ||
+                              EPI == EPI_BIAS_GELU_F32 || EPI == EPI_DGELU_F32);
+    if (!valid) return;
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (kBias) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 4 * j));      // same address in every lane: one broadcast
+        v[4 * j] = __uint_as_float(r[4 * j]) + b4.x;
+        v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + b4.y;
+        v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + b4.z;
+        v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + b4.w;
+    }
+    const size_t off = size_t(row) * p.ldo + col0;
+    auto store16 = [&](__nv_bfloat16* dst) {
+        uint32_t w[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) w[j] = pack_h2<F16>(v[2 * j], v[2 * j + 1]);
+        stg256(dst + off, w);
+        stg256(dst + off + 16, w + 8);
+    };
+    auto store32 = [&](float* dst) {
+        uint32_t w[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) w[j] = __float_as_uint(v[j]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) stg256(dst + off + 8 * j, w + 8 * j);
+    };
+    if (!kF32Out) {
+        if (EPI == EPI_DGELU_BF16) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                if (LPI_H2_ACT && F16 && !p.precise_act) {
+                    const float2 d = h2_quick_gelu_grad(pre[j]);
+                    v[2 * j] *= d.x; v[2 * j + 1] *= d.y;
+                } else {
+                    const float2 z = unpack_h2<F16>(pre[j]);
+                    if (F16 && p.precise_act) { v[2 * j] *= quick_gelu_grad<true>(z.x); v[2 * j + 1] *= quick_gelu_grad<true>(z.y); }
+                    else { v[2 * j] *= quick_gelu_grad<false>(z.x); v[2 * j + 1] *= quick_gelu_grad<false>(z.y); }
+                }
+            }
+        }
+        if (EPI == EPI_BIAS_GELU_BF16) {
+            if (p.out2_bf16) store16(p.out2_bf16);                  // pre-activation, kept for the backward
+            if (F16 && p.precise_act) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = quick_gelu<true>(v[j]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = quick_gelu<false>(v[j]);
+            }
+        }
+        store16(p.out_bf16);
+    } else {
+        if (EPI == EPI_BIAS_RESID_F32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += __uint_as_float(pre[j]);
+        } else if (EPI == EPI_ACC_F32 || EPI == EPI_DGELU_F32) {
+            const float* src = (EPI == EPI_ACC_F32 ? p.out_f32 : p.aux_f32) + off;
+            uint32_t e[32];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) ldg256(src + 8 * j, e + 8 * j);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                if (EPI == EPI_ACC_F32) v[j] += __uint_as_float(e[j]);
+                else v[j] *= quick_gelu_grad<true>(__uint_as_float(e[j]));
+            }
+        }
+        if (EPI == EPI_BIAS_GELU_F32) {
+            if (p.out2_f32) store32(p.out2_f32);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = quick_gelu<true>(v[j]);
+        }
+        store32(p.out_f32);
+        if ((EPI == EPI_BIAS_RESID_F32 || EPI == EPI_ACC_F32) && p.out_bf16) store16(p.out_bf16);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ running top-k (MODE_TOPK)
@@ -683,7 +878,11 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t tmem_base = *tmem_slot;
 
     // ---- work decomposition: a pure function of (cluster_id, rank), re-derived by every role
-    // GEMM : cluster tile t -> (mp = t % num_mp, nt = t / num_mp); this CTA owns rows (2 mp + rank) * 128
+    // GEMM : cluster tile t -> (nt = t % num_n, mp = t / num_n), N fastest: the clusters running at the same time cover all N tiles of
+    //        a few row blocks, so a block of the LARGE operand (A: up to 84 MB of activations) is fetched from HBM once and hit in L2 by
+    //        its other N tiles; the weights (B, <= 4.7 MB) stay L2-resident either way.  (M fastest re-streamed A once per N tile:
+    //        210 MB of DRAM reads for the 84 MB operand of the K = 3072 dgrad, profiles/r2_gemm_vs_cublas.md.)  This CTA owns rows
+    //        (2 mp + rank) * 128
     // TOPK : item i -> (qp = i % num_mp, chunk = i / num_mp); gallery tiles [chunk * tpc, min(num_n, (chunk + 1) * tpc))
     const int total = (MODE == MODE_GEMM) ? num_mp * num_n : num_mp * p.n_chunks;
 
@@ -693,7 +892,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             int stage = 0;
             uint32_t phase = 0, aphase = 0;
             for (int t = cluster_id; t < total; t += n_clusters) {
-                const int mp = t % num_mp, second = t / num_mp;
+                const int mp = (MODE == MODE_GEMM && LPI_RASTER_N) ? t / num_n : t % num_mp, second = (MODE == MODE_GEMM && LPI_RASTER_N) ? t % num_n : t / num_mp;
                 const int m0 = (2 * mp + int(rank)) * BM;
                 int n_begin, n_end;
                 if (MODE == MODE_GEMM) { n_begin = second; n_end = second + 1; }
@@ -735,7 +934,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0, aphase = 0;
             for (int t = cluster_id; t < total; t += n_clusters) {
-                const int second = t / num_mp;
+                const int second = (MODE == MODE_GEMM && LPI_RASTER_N) ? t % num_n : t / num_mp;
                 int n_begin, n_end;
                 if (MODE == MODE_GEMM) { n_begin = second; n_end = second + 1; }
                 else {
@@ -781,7 +980,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                      r_local, p.k, 0, -INFINITY};
         const uint32_t tempty_leader0 = mapa_u32(tempty_bar(0), 0), tempty_leader1 = mapa_u32(tempty_bar(1), 0);
         for (int t = cluster_id; t < total; t += n_clusters) {
-            const int mp = t % num_mp, second = t / num_mp;
+            const int mp = (MODE == MODE_GEMM && LPI_RASTER_N) ? t / num_n : t % num_mp, second = (MODE == MODE_GEMM && LPI_RASTER_N) ? t % num_n : t / num_mp;
             const int m0 = (2 * mp + int(rank)) * BM;
             const int row = m0 + r_local;
             int n_begin, n_end;
@@ -792,20 +991,62 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int nt = n_begin; nt < n_end; ++nt) {
                 const int n0 = nt * BN;
                 constexpr int NCH = BN / 64;                   // 32-column blocks per epilogue warp
-                constexpr bool kPrefetchAux = (MODE == MODE_GEMM) && (EPI == EPI_DGELU_BF16);
+                constexpr bool kPrefetchAux = (MODE == MODE_GEMM) && (EPI == EPI_DGELU_BF16) && !LPI_EPI_DIRECT;
+                constexpr bool kPrefetchResid = (MODE == MODE_GEMM) && (EPI == EPI_BIAS_RESID_F32) && !LPI_EPI_DIRECT;
+                // direct epilogue: this thread's row of the saved pre-activation / residual, two 32-column blocks ahead (the first two are
+                // requested before the accumulator wait)
+                constexpr int NPRE = (EPI == EPI_BIAS_RESID_F32) ? 32 : 16;
+                uint32_t d0[NPRE], d1[NPRE];
+                const bool valid = row < p.M;
+                auto prefetch = [&](int c, uint32_t (&e)[NPRE]) {
+                    if constexpr (EPI == EPI_DGELU_BF16) prefetch_aux_direct(p, row, n0 + c * 32, valid, e);
+                    if constexpr (EPI == EPI_BIAS_RESID_F32) prefetch_resid_direct(p, row, n0 + c * 32, valid, e);
+                };
+                if (MODE == MODE_GEMM && LPI_EPI_DIRECT) {
+                    prefetch(col_half * NCH + 0, d0);
+                    if (NCH > 1) prefetch(col_half * NCH + 1, d1);
+                }
                 uint2 pre0[8], pre1[8];
+                float4 rs0[8], rs1[8];
                 if (kPrefetchAux) {
                     prefetch_aux_block(p, m0 + quad * 32, n0 + (col_half * NCH + 0) * 32, lane, pre0);
                     prefetch_aux_block(p, m0 + quad * 32, n0 + (col_half * NCH + 1) * 32, lane, pre1);
                 }
+                if (kPrefetchResid) {
+                    prefetch_resid_block(p, m0 + quad * 32, n0 + (col_half * NCH + 0) * 32, lane, rs0);
+                    prefetch_resid_block(p, m0 + quad * 32, n0 + (col_half * NCH + 1) * 32, lane, rs1);
+                }
                 mbar_wait(tfull_bar(acc), acc_phase);
                 tc_fence_after();
-                if (MODE == MODE_GEMM) {
-                    auto do_block = [&](int c, const uint2* pre) {
+                if (MODE == MODE_GEMM && LPI_EPI_DIRECT) {
+                    // thread = output row; 32-column blocks straight to global memory (see epilogue_direct)
+                    const int cb = col_half * NCH;
+                    auto block = [&](int c, const uint32_t* pre) {
                         uint32_t r[32];
                         const uint32_t taddr = tmem_base + uint32_t(acc * 256 + c * 32) + (uint32_t(quad * 32) << 16);
                         LPI_TMEM_LD_X32(taddr, r);
                         tmem_ld_wait();
+                        epilogue_direct<EPI, F16>(p, r, row, n0 + c * 32, valid, pre);
+                    };
+                    block(cb + 0, d0);
+                    if (NCH > 2) prefetch(cb + 2, d0);
+                    if (NCH > 1) block(cb + 1, d1);
+                    if (NCH > 3) prefetch(cb + 3, d1);
+                    if (NCH > 2) block(cb + 2, d0);
+                    if (NCH > 3) block(cb + 3, d1);
+                } else if (MODE == MODE_GEMM) {
+                    auto do_block = [&](int c, const uint2* pre, const float4* pre_rs = nullptr) {
+#if defined(LPI_DEBUG_PROBE) && LPI_DEBUG_PROBE == 2
+                        return;                                // timing study: no epilogue at all (results WRONG)
+#endif
+                        uint32_t r[32];
+                        const uint32_t taddr = tmem_base + uint32_t(acc * 256 + c * 32) + (uint32_t(quad * 32) << 16);
+                        LPI_TMEM_LD_X32(taddr, r);
+                        tmem_ld_wait();
+#if defined(LPI_DEBUG_PROBE) && LPI_DEBUG_PROBE == 3
+                        if (r[0] == 0x7fc01234u && r[31] == 0x7fc04321u) p.out_f32[0] = 1.f;      // timing study: TMEM drain only (results WRONG)
+                        return;
+#endif
                         float4* stg = reinterpret_cast<float4*>(smem_gen + C::LIST_OFF) + (warp - 2) * 32 * 8;
                         constexpr bool k16 = (EPI == EPI_BIAS_BF16 || EPI == EPI_BF16 || EPI == EPI_BIAS_GELU_BF16) && LPI_EPI16;
                         if (k16) {
@@ -816,7 +1057,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                 stg[lane * 8 + (j ^ (lane & 7))] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
                                                                                __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
                             __syncwarp();
-                            epilogue_block<EPI, F16>(p, stg, m0 + quad * 32, n0 + c * 32, lane, pre);
+                            epilogue_block<EPI, F16>(p, stg, m0 + quad * 32, n0 + c * 32, lane, pre, pre_rs);
                             __syncwarp();
                         }
                     };
@@ -829,6 +1070,14 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         if (NCH > 3) prefetch_aux_block(p, m0 + quad * 32, n0 + (cb + 3) * 32, lane, pre1);
                         if (NCH > 2) do_block(cb + 2, pre0);
                         if (NCH > 3) do_block(cb + 3, pre1);
+                    } else if (kPrefetchResid) {
+                        const int cb = col_half * NCH;
+                        do_block(cb + 0, nullptr, rs0);
+                        if (NCH > 2) prefetch_resid_block(p, m0 + quad * 32, n0 + (cb + 2) * 32, lane, rs0);
+                        do_block(cb + 1, nullptr, rs1);
+                        if (NCH > 3) prefetch_resid_block(p, m0 + quad * 32, n0 + (cb + 3) * 32, lane, rs1);
+                        if (NCH > 2) do_block(cb + 2, nullptr, rs0);
+                        if (NCH > 3) do_block(cb + 3, nullptr, rs1);
                     } else {
 #pragma unroll 1
                         for (int c = col_half * NCH; c < (col_half + 1) * NCH; ++c) do_block(c, nullptr);

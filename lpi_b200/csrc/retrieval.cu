@@ -22,8 +22,15 @@ __device__ __forceinline__ void warp_best(float& s, int& i, int& owner) {
 }
 
 // One warp per query: the n_parts*k candidates are spread over the lanes; k rounds of warp argbest.
-__global__ void topk_merge_kernel(const float* __restrict__ ps, const int* __restrict__ pi, int n_parts, int nq, int k,
-                                  float* __restrict__ os, int* __restrict__ oi) {
+// Parts may come in groups (one group per rank of an all-gathered exchange buffer): part p lives at
+// (p / parts_per_group) * group_stride + (p % parts_per_group) * nq * k elements from the base pointers.
+// RECALL: the same warp also ranks the query's ground truth in the merged list and bumps the per-task Recall@1/5/10 counters
+// (sprompt.py:559-619) -- the whole tail of a sharded search step (k-way merge over chunks and ranks + bookkeeping) is one launch.
+template <bool RECALL>
+__global__ void topk_merge_kernel(const float* __restrict__ ps, const int* __restrict__ pi, int n_parts, int parts_per_group,
+                                  long long group_stride, int nq, int k, float* __restrict__ os, int* __restrict__ oi,
+                                  const int* __restrict__ gt_ptr, const int* __restrict__ gt_idx, const int* __restrict__ task,
+                                  int n_tasks, int* __restrict__ counts, int* __restrict__ rank_out) {
     const int q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (q >= nq) return;
     const int lane = lane_id();
@@ -31,13 +38,16 @@ __global__ void topk_merge_kernel(const float* __restrict__ ps, const int* __res
     constexpr int PER = 8;                      // up to 256 candidates per query (e.g. 8 shards x 3 chunks x 10)
     float s[PER];
     int id[PER];
+    int g0 = 0, g1 = 0, rank = k;
+    if (RECALL) { g0 = gt_ptr[q]; g1 = gt_ptr[q + 1]; }
 #pragma unroll
     for (int t = 0; t < PER; ++t) {
         const int c = lane + 32 * t;
         if (c < total) {
             const int part = c / k, j = c - part * k;
-            s[t] = ps[(size_t(part) * nq + q) * k + j];
-            id[t] = pi[(size_t(part) * nq + q) * k + j];
+            const size_t off = size_t(part / parts_per_group) * group_stride + (size_t(part % parts_per_group) * nq + q) * k + j;
+            s[t] = ps[off];
+            id[t] = pi[off];
         } else {
             s[t] = -CUDART_INF_F;
             id[t] = 0x7fffffff;
@@ -60,6 +70,21 @@ __global__ void topk_merge_kernel(const float* __restrict__ ps, const int* __res
         if (lane == 0) {
             os[size_t(q) * k + r] = ws;
             oi[size_t(q) * k + r] = wi;
+        }
+        if (RECALL && rank == k) {              // every lane holds the winner: first position whose index is a ground truth of q
+            bool hit = false;
+            for (int g = g0 + lane; g < g1; g += 32) hit |= (gt_idx[g] == wi);
+            if (__any_sync(0xffffffffu, hit)) rank = r;
+        }
+    }
+    if (RECALL && lane == 0) {
+        if (rank_out) rank_out[q] = rank;
+        const int t = task ? task[q] : 0;
+        if (t >= 0 && t < n_tasks) {
+            if (rank < k && rank < 1) atomicAdd(&counts[4 * t + 0], 1);
+            if (rank < k && rank < 5) atomicAdd(&counts[4 * t + 1], 1);
+            if (rank < k && rank < 10) atomicAdd(&counts[4 * t + 2], 1);
+            atomicAdd(&counts[4 * t + 3], 1);
         }
     }
 }
@@ -187,9 +212,29 @@ extern "C" int lpi_topk_merge(const float* part_scores, const int* part_idx, int
     if (k < 1 || n_parts < 1 || long(n_parts) * k > 256)
         return set_error(LPI_ERR_ARG, "topk_merge: n_parts*k=%ld must be in [1,256]", long(n_parts) * k);
     const int threads = 256, wpb = threads / 32;
-    topk_merge_kernel<<<(n_queries + wpb - 1) / wpb, threads, 0, static_cast<cudaStream_t>(stream)>>>(
-        part_scores, part_idx, n_parts, n_queries, k, out_scores, out_idx);
+    topk_merge_kernel<false><<<(n_queries + wpb - 1) / wpb, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+        part_scores, part_idx, n_parts, n_parts, 0, n_queries, k, out_scores, out_idx, nullptr, nullptr, nullptr, 0, nullptr, nullptr);
     return check_launch("topk_merge");
+}
+
+extern "C" int lpi_topk_merge_recall(const float* part_scores, const int* part_idx, int n_parts, int parts_per_group,
+                                     long long group_stride, int n_queries, int k, float* out_scores, int* out_idx,
+                                     const int* gt_ptr, const int* gt_idx, const int* task_of_query, int n_tasks, int* counts,
+                                     int* rank_out, void* stream) {
+    if (n_tasks < 1) return set_error(LPI_ERR_ARG, "topk_merge_recall: n_tasks=%d", n_tasks);
+    if (k < 1 || n_parts < 1 || long(n_parts) * k > 256)
+        return set_error(LPI_ERR_ARG, "topk_merge_recall: n_parts*k=%ld must be in [1,256]", long(n_parts) * k);
+    if (parts_per_group < 1 || n_parts % parts_per_group)
+        return set_error(LPI_ERR_ARG, "topk_merge_recall: n_parts=%d is not a multiple of parts_per_group=%d", n_parts, parts_per_group);
+    if (!gt_ptr || !gt_idx || !counts) return set_error(LPI_ERR_ARG, "topk_merge_recall: ground truth / counters missing");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaMemsetAsync(counts, 0, sizeof(int) * 4 * n_tasks, st);
+    if (n_queries <= 0) return LPI_OK;
+    const int threads = 256, wpb = threads / 32;
+    topk_merge_kernel<true><<<(n_queries + wpb - 1) / wpb, threads, 0, st>>>(part_scores, part_idx, n_parts, parts_per_group, group_stride,
+                                                                           n_queries, k, out_scores, out_idx, gt_ptr, gt_idx,
+                                                                           task_of_query, n_tasks, counts, rank_out);
+    return check_launch("topk_merge_recall");
 }
 
 extern "C" int lpi_topk_rows_f32(const float* scores, int n_rows, int n_cols, long long ld, int k, float* out_scores,

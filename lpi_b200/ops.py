@@ -95,7 +95,8 @@ SEED_MIN_GALLERY = 131072    # below this the warm-up is not worth a second laun
 
 
 def sim_topk(q: torch.Tensor, g: torch.Tensor, k: int = 10, gallery_offset: int = 0, n_chunks: int = 0,
-             merge: bool = True, seed_rows: Optional[int] = None, init_thr: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+             merge: bool = True, seed_rows: Optional[int] = None, init_thr: Optional[torch.Tensor] = None,
+             out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """Top-k gallery rows per query by dot product; q [nq,dim], g [ng,dim] bf16.
     Returns (scores fp32, global idx int32), [nq,k] when merged else [n_chunks,nq,k].
     seed_rows: None = automatic (a pre-pass over the first SEED_ROWS rows of large galleries supplies per-query thresholds, which
@@ -103,7 +104,8 @@ def sim_topk(q: torch.Tensor, g: torch.Tensor, k: int = 10, gallery_offset: int 
     init_thr: [nq] fp32, per query a score that at least k rows of the same logical gallery are known to reach (e.g. the running
     maximum of the k-th scores of the chunks of a streamed gallery seen so far); used instead of a pre-pass.  The lists returned then
     hold only candidates that can still enter the union's top-k (possibly fewer than k; the rest is (-inf, INT_MAX)): merge them with
-    the lists that produced the threshold."""
+    the lists that produced the threshold.
+    out: (scores fp32, idx int32) buffers of shape [n_chunks, nq, k] for the per-chunk lists (e.g. the two halves of one exchange buffer)."""
     _lib.require_device()
     _chk(q, torch.bfloat16, "q")
     _chk(g, torch.bfloat16, "g")
@@ -126,8 +128,15 @@ def sim_topk(q: torch.Tensor, g: torch.Tensor, k: int = 10, gallery_offset: int 
         call("sim_topk_seed_bf16", ptr(q), ptr(g), nq, seed_rows, dim, k, ptr(seed_scores), ptr(seed_idx), stream_ptr())
         _count()
         thr_ptr, thr_stride = C.c_void_p(seed_scores.data_ptr() + 4 * (k - 1)), k
-    ps = torch.empty(n_chunks, nq, k, device=q.device, dtype=torch.float32)
-    pi = torch.empty(n_chunks, nq, k, device=q.device, dtype=torch.int32)
+    if out is not None:
+        ps, pi = out
+        _chk(ps, torch.float32, "out scores")
+        _chk(pi, torch.int32, "out idx")
+        if tuple(ps.shape) != (n_chunks, nq, k) or tuple(pi.shape) != (n_chunks, nq, k):
+            raise _lib.LpiError(f"out buffers must be [{n_chunks}, {nq}, {k}]")
+    else:
+        ps = torch.empty(n_chunks, nq, k, device=q.device, dtype=torch.float32)
+        pi = torch.empty(n_chunks, nq, k, device=q.device, dtype=torch.int32)
     call("sim_topk_bf16", ptr(q), ptr(g), nq, ng, dim, k, C.c_longlong(gallery_offset), n_chunks, thr_ptr, thr_stride, ptr(ps), ptr(pi),
          stream_ptr())
     _count()
@@ -155,6 +164,30 @@ def topk_merge(part_scores: torch.Tensor, part_idx: torch.Tensor) -> Tuple[torch
     call("topk_merge", ptr(part_scores), ptr(part_idx), n_parts, nq, k, ptr(os_), ptr(oi), stream_ptr())
     _count()
     return os_, oi
+
+
+def topk_merge_recall(packed: torch.Tensor, gt_ptr: torch.Tensor, gt_idx: torch.Tensor, task: torch.Tensor, n_tasks: int,
+                      want_rank: bool = False):
+    """The tail of a (sharded) search step in ONE launch: k-way merge + Recall@K counters.
+    packed: int32 [G, 2, c, nq, k] -- per group (rank) the c per-chunk score lists (fp32 bit patterns) followed by the c index lists,
+    i.e. exactly what an all-gather of every rank's [2, c, nq, k] exchange buffer produces.
+    Returns (scores [nq,k] fp32, idx [nq,k] int32, counts [n_tasks,4] int32[, rank [nq] int32])."""
+    _lib.require_device()
+    _chk(packed, torch.int32, "packed")
+    for t, n in ((gt_ptr, "gt_ptr"), (gt_idx, "gt_idx"), (task, "task")):
+        _chk(t, torch.int32, n)
+    G, two, c, nq, k = packed.shape
+    if two != 2:
+        raise _lib.LpiError("packed must be [G, 2, c, nq, k]")
+    os_ = torch.empty(nq, k, device=packed.device, dtype=torch.float32)
+    oi = torch.empty(nq, k, device=packed.device, dtype=torch.int32)
+    counts = torch.empty(n_tasks, 4, device=packed.device, dtype=torch.int32)
+    rank = torch.empty(nq, device=packed.device, dtype=torch.int32) if want_rank else None
+    idx_base = C.c_void_p(packed.data_ptr() + 4 * c * nq * k)
+    call("topk_merge_recall", ptr(packed), idx_base, G * c, c, C.c_longlong(2 * c * nq * k), nq, k, ptr(os_), ptr(oi), ptr(gt_ptr), ptr(gt_idx),
+         ptr(task), n_tasks, ptr(counts), ptr(rank), stream_ptr())
+    _count()
+    return (os_, oi, counts, rank) if want_rank else (os_, oi, counts)
 
 
 def topk_rows(scores: torch.Tensor, k: int = 10) -> Tuple[torch.Tensor, torch.Tensor]:

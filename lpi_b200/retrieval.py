@@ -145,6 +145,30 @@ def merge_across_ranks(scores: torch.Tensor, idx: torch.Tensor, group) -> Tuple[
     return ops.topk_merge(*gather_candidates(scores, idx, group))
 
 
+def exchange_buffer(n_chunks: int, n_queries: int, k: int, device) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """One allocation holding a rank's per-chunk candidate lists the way the exchange wants them: int32 [2, c, Q, k] = the c score
+    lists (fp32 bit patterns) followed by the c index lists.  Returns (buffer, scores view fp32 [c,Q,k], idx view int32 [c,Q,k]);
+    pass the views to `ops.sim_topk(..., merge=False, out=(scores, idx))`."""
+    buf = torch.empty(2, n_chunks, n_queries, k, device=device, dtype=torch.int32)
+    return buf, buf[0].view(torch.float32), buf[1]
+
+
+def merge_recall(buf: torch.Tensor, gt_ptr: torch.Tensor, gt_idx: torch.Tensor, task: torch.Tensor, n_tasks: int, group=None,
+                 want_rank: bool = False):
+    """Tail of a gallery-sharded search step: ONE all-gather of every rank's exchange buffer (scores and indices of all its chunks
+    together, 2 * c * Q * k * 4 bytes per rank) and ONE kernel that merges the world * c lists per query by (score desc, index asc)
+    and counts Recall@1/5/10 per task.  -> (scores [Q,k], idx [Q,k], counts [n_tasks,4][, rank [Q]])."""
+    packed = buf.unsqueeze(0)
+    if group is not None:
+        import torch.distributed as dist
+
+        world = dist.get_world_size(group)
+        if world > 1:
+            packed = torch.empty(world, *buf.shape, device=buf.device, dtype=buf.dtype)
+            dist.all_gather_into_tensor(packed, buf.contiguous(), group=group)
+    return ops.topk_merge_recall(packed.contiguous(), gt_ptr, gt_idx, task, n_tasks, want_rank)
+
+
 def itm_eval_features(image_feats: torch.Tensor, text_feats: torch.Tensor, txt2img, img2txt, category_i, category_t,
                       task_num: int, precision: str = "fp32", group=None) -> Dict:
     """Same result as `itm_eval((I @ T^T), (I @ T^T)^T, ...)` (sprompt.py:509,544-546) without the score

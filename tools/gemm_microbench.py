@@ -1,4 +1,4 @@
-"""Encoder GEMM shapes of one training step (8 forward + 8 dgrad, vision bf16 + text fp16) at B = 64 and B = 256: this repo's kernel WITH the
+"""Encoder GEMM shapes of one training step (8 forward + 8 dgrad, vision fp16 (or bf16) + text fp16) at B = 64 and B = 256: this repo's kernel WITH the
 fused epilogue the step uses, against cuBLAS (torch.matmul on the same 16-bit operands, no epilogue) on the same box.
 CUDA events, 20 launches after 5 warm-ups; between shapes nothing else runs.  Output: profiles/r2_gemm_microbench.txt
 
@@ -27,10 +27,10 @@ def time_us(fn, iters=20, warm=5):
     return e0.elapsed_time(e1) / iters * 1e3
 
 
-def shapes(B, text_len):
+def shapes(B, text_len, vision_dtype=torch.float16):
     Mv, Mt = B * 213, B * text_len
     out = []
-    for tower, M, D, h in (("vision", Mv, 768, torch.bfloat16), ("text", Mt, 512, torch.float16)):
+    for tower, M, D, h in (("vision", Mv, 768, vision_dtype), ("text", Mt, 512, torch.float16)):
         out += [
             (tower, "qkv       fwd", M, 3 * D, D, ops.EPI_BIAS_BF16, h),
             (tower, "out-proj  fwd", M, D, D, ops.EPI_BIAS_RESID_F32, h),
@@ -48,13 +48,14 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batches", default="64,256")
     ap.add_argument("--text-len", type=int, default=77)
+    ap.add_argument("--vision-dtype", default="fp16", choices=["fp16", "bf16"])
     a = ap.parse_args()
     dev = torch.device("cuda")
     print(f"# {torch.cuda.get_device_name(0)}; ours = lpi_gemm_{{bf16,f16}} with the fused epilogue; cuBLAS = torch.matmul(a, w.t()) same operands, no epilogue")
     print(f"# {'tower':6s} {'gemm':14s} {'M':>6s} {'N':>5s} {'K':>5s} | {'ours us':>8s} {'TFLOP/s':>8s} | {'cuBLAS us':>9s} {'TFLOP/s':>8s} | ours/cuBLAS")
     for B in [int(x) for x in a.batches.split(",")]:
         tot_o = tot_c = tot_f = 0.0
-        for tower, name, M, N, K, epi, h in shapes(B, a.text_len):
+        for tower, name, M, N, K, epi, h in shapes(B, a.text_len, torch.float16 if a.vision_dtype == "fp16" else torch.bfloat16):
             g = torch.Generator(device=dev).manual_seed(1)
             x = torch.randn(M, K, device=dev, generator=g).to(h)
             w = (torch.randn(N, K, device=dev, generator=g) * K ** -0.5).to(h)
