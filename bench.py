@@ -222,18 +222,20 @@ def run_b200(args):
 
     kern_events = []
 
+    n_chunks = ops.sim_topk_chunks(nq, hi - lo)
+    xbuf, xs, xi = R.exchange_buffer(n_chunks, nq, TOPK, dev)     # this rank's per-chunk lists, laid out for the one all-gather
+
     def step(record=False):
+        """threshold pre-pass + scoring pass (top-k in the GEMM epilogue, chunks sharing their thresholds) -> [N > 1: ONE all-gather of the
+        exchange buffer] -> ONE kernel: k-way merge over chunks and ranks + Recall@1/5/10 counters."""
         if record:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-        ps, pi = ops.sim_topk(q, shard, TOPK, lo, merge=False)
+        ops.sim_topk(q, shard, TOPK, lo, n_chunks, merge=False, out=(xs, xi))
         if record:
             e1.record()
             kern_events.append((e0, e1))
-        sc, ix = ops.topk_merge(ps, pi) if ps.shape[0] > 1 else (ps[0], pi[0])
-        if world > 1:
-            sc, ix = R.merge_across_ranks(sc, ix, group)
-        counts = ops.recall_counts(ix, ptr, idx, task, 1)
+        sc, ix, counts = R.merge_recall(xbuf, ptr, idx, task, 1, group)
         return sc, ix, counts
 
     def barrier():
@@ -320,10 +322,8 @@ def run_b200(args):
     def e2e_resident_step():
         """queries in (pinned host), lists + counts out; the gallery shard stays resident in HBM."""
         q_dev.copy_(q_host, non_blocking=True)
-        s_, i_ = ops.sim_topk(q_dev, shard, TOPK, lo)
-        if world > 1:
-            s_, i_ = R.merge_across_ranks(s_, i_, group)
-        c_ = ops.recall_counts(i_, ptr, idx, task, 1)
+        ops.sim_topk(q_dev, shard, TOPK, lo, n_chunks, merge=False, out=(xs, xi))
+        s_, i_, c_ = R.merge_recall(xbuf, ptr, idx, task, 1, group)
         out_ix.copy_(i_, non_blocking=True)
         out_counts.copy_(c_, non_blocking=True)
         return c_

@@ -81,6 +81,11 @@ int lpi_sim_topk_chunks(int n_queries, int n_gallery, int* n_chunks_out);
 int lpi_sim_topk_bf16(const void* Q, const void* G, int n_queries, int n_gallery, int dim, int k,
                       long long gallery_offset, int n_chunks, const float* init_thr, int init_thr_stride,
                       float* part_scores, int* part_idx, void* stream);
+/* Cooperative thresholds: shared_thr [n_queries] fp32 is read and written -- in: a score >= k gallery rows are known to reach per query
+ * (or -inf); out: the best k-th score any chunk of the launch reached.  Same merged top-k as lpi_sim_topk_bf16, fewer sorted insertions
+ * (the chunks of one launch exchange their k-th scores through it); per-chunk lists may hold < k entries (rest: -inf / INT_MAX). */
+int lpi_sim_topk_coop_bf16(const void* Q, const void* G, int n_queries, int n_gallery, int dim, int k, long long gallery_offset,
+                           int n_chunks, float* shared_thr, float* part_scores, int* part_idx, void* stream);
 /* Threshold pre-pass for lpi_sim_topk_bf16: seed_scores [n_queries, k] = the k largest per-tile (256 rows) maxima over the first
  * n_rows gallery rows (seed_idx_ws [n_queries, k] is scratch).  `seed_scores + (k - 1)` with init_thr_stride = k is then a valid
  * init_thr: k distinct rows reach it.  One candidate per tile keeps the pass MMA-bound. */

@@ -35,6 +35,12 @@ constexpr int TOPK_MAX = 16;
 #ifndef LPI_H2_ACT
 #define LPI_H2_ACT 1         // fp16 towers: (d)QuickGELU on packed halves (0 = fp32 arithmetic as in the bf16 tower; A/B builds)
 #endif
+#ifndef LPI_F16_PRECISE_ACT
+#define LPI_F16_PRECISE_ACT 0   // fp16 towers: 1 = ex2 + rcp sigmoid in fp32 (2 MUFU ops per element) for precision studies; a build-time switch so
+#endif                          // that the shipped epilogues carry one activation path, not a runtime branch per element
+#ifndef LPI_AUX_LDCS
+#define LPI_AUX_LDCS 0      // 1 = evict-first loads of the saved pre-activation (measured slower: 75.7 vs 72.5 us on the dGELU GEMM)
+#endif
 #ifndef LPI_EPI_DIRECT
 #define LPI_EPI_DIRECT 0     // pair GEMM epilogue: 1 = accumulator rows straight to global memory with 256-bit accesses (no smem staging)
 #endif
@@ -66,6 +72,7 @@ struct GemmArgs {
     int seed_mode;                 // 1: keep the top-k of the per-TILE maxima only (threshold pre-pass: one candidate per 256 gallery rows)
     int init_thr_stride;           // element stride of init_thr (lets the k-th column of a [M, k] list be used in place)
     const float* init_thr;         // [M] or null: per-query score every kept candidate must reach (seeded by a pre-pass over a gallery sample)
+    float* shared_thr;             // [M] or null: thresholds SHARED by the work items of one launch (cooperative mode, see coop_* below)
     float* topk_scores;            // [n_chunks, M, k]
     int* topk_idx;                 // [n_chunks, M, k]
 };
@@ -271,14 +278,14 @@ __device__ __forceinline__ void epilogue_block(const GemmArgs& p, const float4* 
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                if (LPI_H2_ACT && F16 && !p.precise_act) {                  // packed-half derivative (see h2_quick_gelu_grad)
+                if (LPI_H2_ACT && F16 && !bool(LPI_F16_PRECISE_ACT)) {                  // packed-half derivative (see h2_quick_gelu_grad)
                     const float2 d0 = h2_quick_gelu_grad(e[i].x), d1 = h2_quick_gelu_grad(e[i].y);
                     v[i].x *= d0.x; v[i].y *= d0.y; v[i].z *= d1.x; v[i].w *= d1.y;
                     continue;
                 }
                 const float2 z0 = unpack_h2<F16>(e[i].x);
                 const float2 z1 = unpack_h2<F16>(e[i].y);
-                if (F16 && p.precise_act) {
+                if (F16 && bool(LPI_F16_PRECISE_ACT)) {
                     v[i].x *= quick_gelu_grad<true>(z0.x); v[i].y *= quick_gelu_grad<true>(z0.y);
                     v[i].z *= quick_gelu_grad<true>(z1.x); v[i].w *= quick_gelu_grad<true>(z1.y);
                 } else {
@@ -293,7 +300,7 @@ __device__ __forceinline__ void epilogue_block(const GemmArgs& p, const float4* 
             const size_t off = base + size_t(i * 4) * p.ldo;
             if (EPI == EPI_BIAS_GELU_BF16) {
                 if (p.out2_bf16) *reinterpret_cast<uint2*>(p.out2_bf16 + off) = make_uint2(pack_h2<F16>(v[i].x, v[i].y), pack_h2<F16>(v[i].z, v[i].w));
-                if (F16 && p.precise_act) v[i] = make_float4(quick_gelu<true>(v[i].x), quick_gelu<true>(v[i].y), quick_gelu<true>(v[i].z), quick_gelu<true>(v[i].w));
+                if (F16 && bool(LPI_F16_PRECISE_ACT)) v[i] = make_float4(quick_gelu<true>(v[i].x), quick_gelu<true>(v[i].y), quick_gelu<true>(v[i].z), quick_gelu<true>(v[i].w));
                 else v[i] = make_float4(quick_gelu<false>(v[i].x), quick_gelu<false>(v[i].y), quick_gelu<false>(v[i].z), quick_gelu<false>(v[i].w));
             }
             *reinterpret_cast<uint2*>(p.out_bf16 + off) = make_uint2(pack_h2<F16>(v[i].x, v[i].y), pack_h2<F16>(v[i].z, v[i].w));
@@ -340,7 +347,7 @@ __device__ __forceinline__ void epilogue_block16(const GemmArgs& p, const uint32
         }
         __syncwarp();
     };
-    if (LPI_H2_ACT && EPI == EPI_BIAS_GELU_BF16 && F16 && !p.precise_act) {
+    if (LPI_H2_ACT && EPI == EPI_BIAS_GELU_BF16 && F16 && !bool(LPI_F16_PRECISE_ACT)) {
         // fp16 tower: pack the pre-activation once, store it, then the activation on the packed halves
         uint32_t w[16];
 #pragma unroll
@@ -368,7 +375,7 @@ __device__ __forceinline__ void epilogue_block16(const GemmArgs& p, const uint32
     }
     if (EPI == EPI_BIAS_GELU_BF16) {
         if (p.out2_bf16) stage_and_store(p.out2_bf16, true);    // pre-activation, kept for the backward
-        if (F16 && p.precise_act) {
+        if (F16 && bool(LPI_F16_PRECISE_ACT)) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = quick_gelu<true>(v[j]);
         } else {
@@ -389,7 +396,11 @@ __device__ __forceinline__ void prefetch_aux_block(const GemmArgs& p, int row0, 
     const size_t base = size_t(row0 + rsub) * p.ldo + col0 + c * 4;
 #pragma unroll
     for (int i = 0; i < 8; ++i)
+#if LPI_AUX_LDCS
         e[i] = (i * 4 + rsub < rows) ? __ldcs(reinterpret_cast<const uint2*>(p.aux_bf16 + base + size_t(i * 4) * p.ldo)) : make_uint2(0u, 0u);   // read once: evict-first
+#else
+        e[i] = (i * 4 + rsub < rows) ? __ldg(reinterpret_cast<const uint2*>(p.aux_bf16 + base + size_t(i * 4) * p.ldo)) : make_uint2(0u, 0u);
+#endif
 }
 
 // Same idea for the fp32 residual of EPI_BIAS_RESID_F32 (out-proj / c_proj forward): the residual stream was written one or two kernels
@@ -470,19 +481,19 @@ __device__ __forceinline__ void epilogue_direct(const GemmArgs& p, const uint32_
         if (EPI == EPI_DGELU_BF16) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                if (LPI_H2_ACT && F16 && !p.precise_act) {
+                if (LPI_H2_ACT && F16 && !bool(LPI_F16_PRECISE_ACT)) {
                     const float2 d = h2_quick_gelu_grad(pre[j]);
                     v[2 * j] *= d.x; v[2 * j + 1] *= d.y;
                 } else {
                     const float2 z = unpack_h2<F16>(pre[j]);
-                    if (F16 && p.precise_act) { v[2 * j] *= quick_gelu_grad<true>(z.x); v[2 * j + 1] *= quick_gelu_grad<true>(z.y); }
+                    if (F16 && bool(LPI_F16_PRECISE_ACT)) { v[2 * j] *= quick_gelu_grad<true>(z.x); v[2 * j + 1] *= quick_gelu_grad<true>(z.y); }
                     else { v[2 * j] *= quick_gelu_grad<false>(z.x); v[2 * j + 1] *= quick_gelu_grad<false>(z.y); }
                 }
             }
         }
         if (EPI == EPI_BIAS_GELU_BF16) {
             if (p.out2_bf16) store16(p.out2_bf16);                  // pre-activation, kept for the backward
-            if (F16 && p.precise_act) {
+            if (F16 && bool(LPI_F16_PRECISE_ACT)) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = quick_gelu<true>(v[j]);
             } else {
@@ -553,6 +564,19 @@ __device__ __forceinline__ float float_prev(float x) {
     if (x == 0.f) return __uint_as_float(0x80000001u);
     return __uint_as_float(b + 1);
 }
+
+// Cooperative thresholds.  A gallery shard is cut into chunks for load balance, and every (query tile, chunk) item used to warm its
+// top-k lists up alone: with the exact final thresholds handed in the 625 k-row shard of the 8-GPU run takes 10.7 ms, with the seeded
+// ones 12.2 ms (profiles/r2_scorer_fixed_cost.txt) -- the difference is sorted insertions of candidates that another chunk's list
+// already rules out.  So the items of one launch share one fp32 per query row in global memory: a row publishes its own k-th score
+// whenever that improves (k gallery rows reach it, so it bounds the final k-th score from below) and polls the shared value once per
+// gallery tile.  Whatever an item then drops is below a score k rows of the union reach, so the MERGED result is unchanged; the
+// per-chunk lists themselves depend on timing and may hold fewer than k entries (rest: -inf / INT_MAX), as with init_thr.
+__device__ __forceinline__ void coop_publish(float* addr, float v) {      // atomic max on fp32 through the integer ordering
+    if (v >= 0.f) atomicMax(reinterpret_cast<int*>(addr), __float_as_int(v));
+    else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+__device__ __forceinline__ float coop_poll(const float* addr) { return __ldcg(addr); }      // L2: never a stale L1 line
 
 // maximum of one 64-column accumulator block (ragged tail masked) -- the whole epilogue of the threshold pre-pass
 template <int NCOL>
@@ -885,6 +909,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     //        (2 mp + rank) * 128
     // TOPK : item i -> (qp = i % num_mp, chunk = i / num_mp); gallery tiles [chunk * tpc, min(num_n, (chunk + 1) * tpc))
     const int total = (MODE == MODE_GEMM) ? num_mp * num_n : num_mp * p.n_chunks;
+    // TOPK item order stays chunk-major (concurrent clusters stream the same gallery region) with cooperative thresholds too: the
+    // chunk-fastest order, which lets the chunks of one query tile warm each other up from the first wave on, measured 7 % SLOWER
+    // (625 k rows: 12.10 vs 11.34 ms; the exact-threshold run slows down as well, i.e. it is the lost L2 locality of the gallery stream)
+    constexpr bool topk_qmajor = false;
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer (one thread per CTA)
@@ -892,7 +920,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             int stage = 0;
             uint32_t phase = 0, aphase = 0;
             for (int t = cluster_id; t < total; t += n_clusters) {
-                const int mp = (MODE == MODE_GEMM && LPI_RASTER_N) ? t / num_n : t % num_mp, second = (MODE == MODE_GEMM && LPI_RASTER_N) ? t % num_n : t / num_mp;
+                const int mp = (MODE == MODE_GEMM) ? (LPI_RASTER_N ? t / num_n : t % num_mp) : (topk_qmajor ? t / p.n_chunks : t % num_mp);
+                const int second = (MODE == MODE_GEMM) ? (LPI_RASTER_N ? t % num_n : t / num_mp) : (topk_qmajor ? t % p.n_chunks : t / num_mp);
                 const int m0 = (2 * mp + int(rank)) * BM;
                 int n_begin, n_end;
                 if (MODE == MODE_GEMM) { n_begin = second; n_end = second + 1; }
@@ -934,7 +963,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0, aphase = 0;
             for (int t = cluster_id; t < total; t += n_clusters) {
-                const int second = (MODE == MODE_GEMM && LPI_RASTER_N) ? t % num_n : t / num_mp;
+                const int second = (MODE == MODE_GEMM) ? (LPI_RASTER_N ? t % num_n : t / num_mp) : (topk_qmajor ? t % p.n_chunks : t / num_mp);
                 int n_begin, n_end;
                 if (MODE == MODE_GEMM) { n_begin = second; n_end = second + 1; }
                 else {
@@ -980,7 +1009,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                      r_local, p.k, 0, -INFINITY};
         const uint32_t tempty_leader0 = mapa_u32(tempty_bar(0), 0), tempty_leader1 = mapa_u32(tempty_bar(1), 0);
         for (int t = cluster_id; t < total; t += n_clusters) {
-            const int mp = (MODE == MODE_GEMM && LPI_RASTER_N) ? t / num_n : t % num_mp, second = (MODE == MODE_GEMM && LPI_RASTER_N) ? t % num_n : t / num_mp;
+            const int mp = (MODE == MODE_GEMM) ? (LPI_RASTER_N ? t / num_n : t % num_mp) : (topk_qmajor ? t / p.n_chunks : t % num_mp);
+                const int second = (MODE == MODE_GEMM) ? (LPI_RASTER_N ? t % num_n : t / num_mp) : (topk_qmajor ? t % p.n_chunks : t / num_mp);
             const int m0 = (2 * mp + int(rank)) * BM;
             const int row = m0 + r_local;
             int n_begin, n_end;
@@ -988,9 +1018,13 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             else { n_begin = second * p.tiles_per_chunk; n_end = min(num_n, n_begin + p.tiles_per_chunk); }
             tk.thr = (MODE == MODE_TOPK && p.init_thr && row < p.M) ? float_prev(p.init_thr[size_t(row) * p.init_thr_stride]) : -INFINITY;
             tk.cnt = 0;
+            const bool coop = (MODE == MODE_TOPK) && p.shared_thr != nullptr && !p.seed_mode && row < p.M;
+            float coop_floor = tk.thr, coop_pub = -INFINITY;   // best outside bound seen / own k-th score last published
             for (int nt = n_begin; nt < n_end; ++nt) {
                 const int n0 = nt * BN;
                 constexpr int NCH = BN / 64;                   // 32-column blocks per epilogue warp
+                float coop_in = -INFINITY;
+                if (coop) coop_in = coop_poll(p.shared_thr + row);     // in flight across the accumulator wait
                 constexpr bool kPrefetchAux = (MODE == MODE_GEMM) && (EPI == EPI_DGELU_BF16) && !LPI_EPI_DIRECT;
                 constexpr bool kPrefetchResid = (MODE == MODE_GEMM) && (EPI == EPI_BIAS_RESID_F32) && !LPI_EPI_DIRECT;
                 // direct epilogue: this thread's row of the saved pre-activation / residual, two 32-column blocks ahead (the first two are
@@ -1084,6 +1118,11 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     }
                 } else {
                     float tmax = -INFINITY;
+                    if (coop) {
+                        coop_floor = fmaxf(coop_floor, float_prev(coop_in));    // "v > float_prev(s)" == "v >= s": ties with the bound stay in
+                        tk.thr = fmaxf(tk.thr, coop_floor);
+                    }
+                    const float thr_before = tk.thr;
 #pragma unroll 1
                     for (int c = 0; c < BN / 64; ++c) {
                         uint32_t r[64];
@@ -1097,6 +1136,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         const TopkCT ct = topk_insert(tk.sc, tk.id, tk.row, tk.k, tk.cnt, tk.thr, tmax, n0);
                         tk.cnt = ct.cnt;
                         tk.thr = ct.thr;
+                    }
+                    if (coop && tk.cnt == tk.k && tk.thr != thr_before) {
+                        // an insertion into a full list leaves thr = the list's own k-th score: publish it if it improved, and keep
+                        // filtering with the better of it and the outside bound
+                        if (tk.thr > coop_pub) { coop_pub = tk.thr; coop_publish(p.shared_thr + row, tk.thr); }
+                        tk.thr = fmaxf(tk.thr, coop_floor);
                     }
                 }
                 tc_fence_before();
@@ -1318,12 +1363,7 @@ static int gemm_entry(int op, const void* A, const void* B, int M, int N, int K,
     GemmArgs a{};
     a.M = M; a.N = N; a.K = K; a.epi = epi; a.ldo = ldo;
     {
-        static int precise = -1;
-        if (precise < 0) {
-            const char* e = getenv("LPI_F16_PRECISE_ACT");
-            precise = (e && e[0] == '1') ? 1 : 0;
-        }
-        a.precise_act = precise;
+        a.precise_act = LPI_F16_PRECISE_ACT;
 #ifdef LPI_DEBUG_PROBE
         // timing-study build only (never the shipped library): a stray environment variable must not be able to corrupt results
         static int probe = -1;
@@ -1417,7 +1457,8 @@ extern "C" int lpi_sim_topk_chunks(int n_queries, int n_gallery, int* n_chunks_o
 }
 
 static int sim_topk_impl(const void* Q, const void* G, int n_queries, int n_gallery, int dim, int k, long long gallery_offset, int n_chunks,
-                         const float* init_thr, int init_thr_stride, int seed_mode, float* part_scores, int* part_idx, void* stream) {
+                         const float* init_thr, int init_thr_stride, int seed_mode, float* part_scores, int* part_idx, void* stream,
+                         float* shared_thr = nullptr) {
     if (n_queries <= 0 || n_gallery <= 0) return set_error(LPI_ERR_ARG, "sim_topk: empty problem");
     if (dim % BK) return set_error(LPI_ERR_ARG, "sim_topk: dim=%d must be a multiple of %d", dim, BK);
     if (k < 1 || k > TOPK_MAX) return set_error(LPI_ERR_ARG, "sim_topk: k=%d out of range [1,%d]", k, TOPK_MAX);
@@ -1439,6 +1480,7 @@ static int sim_topk_impl(const void* Q, const void* G, int n_queries, int n_gall
     a.seed_mode = seed_mode;
     a.init_thr = init_thr;
     a.init_thr_stride = init_thr_stride > 0 ? init_thr_stride : 1;
+    a.shared_thr = shared_thr;
     a.topk_scores = part_scores;
     a.topk_idx = part_idx;
     const int sms = num_sms();
@@ -1457,6 +1499,18 @@ extern "C" int lpi_sim_topk_bf16(const void* Q, const void* G, int n_queries, in
                                  int* part_idx, void* stream) {
     return sim_topk_impl(Q, G, n_queries, n_gallery, dim, k, gallery_offset, n_chunks, init_thr, init_thr_stride, 0, part_scores, part_idx,
                          stream);
+}
+
+// Cooperative variant: `shared_thr` [n_queries] fp32 is read AND written -- on entry a score that at least k rows of the logical gallery
+// are known to reach per query (a seed / the k-th scores of earlier chunks, or -inf), on exit the best k-th score any chunk of this
+// launch reached.  The work items of the launch exchange their thresholds through it (see coop_publish): same merged result, fewer
+// sorted insertions; the per-chunk lists may hold fewer than k entries.  Needs the CTA-pair kernel (dim <= 512).
+extern "C" int lpi_sim_topk_coop_bf16(const void* Q, const void* G, int n_queries, int n_gallery, int dim, int k,
+                                      long long gallery_offset, int n_chunks, float* shared_thr, float* part_scores, int* part_idx,
+                                      void* stream) {
+    if (!shared_thr) return set_error(LPI_ERR_ARG, "sim_topk_coop: shared_thr is null");
+    return sim_topk_impl(Q, G, n_queries, n_gallery, dim, k, gallery_offset, n_chunks, shared_thr, 1, 0, part_scores, part_idx, stream,
+                         shared_thr);
 }
 
 // Threshold pre-pass: seed_scores[q, 0..k) = the k largest per-tile (256 gallery rows) maxima of query q over the first n_rows rows.

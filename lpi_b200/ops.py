@@ -92,11 +92,12 @@ import os as _os
 
 SEED_ROWS = int(_os.environ.get("LPI_SEED_ROWS", "16384"))   # gallery rows scored first to seed the per-query thresholds of the main pass
 SEED_MIN_GALLERY = 131072    # below this the warm-up is not worth a second launch
+COOP_THRESHOLDS = _os.environ.get("LPI_COOP_THR", "1") != "0"   # chunks of one launch share their per-query thresholds (see sim_topk)
 
 
 def sim_topk(q: torch.Tensor, g: torch.Tensor, k: int = 10, gallery_offset: int = 0, n_chunks: int = 0,
              merge: bool = True, seed_rows: Optional[int] = None, init_thr: Optional[torch.Tensor] = None,
-             out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+             out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, coop: Optional[bool] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """Top-k gallery rows per query by dot product; q [nq,dim], g [ng,dim] bf16.
     Returns (scores fp32, global idx int32), [nq,k] when merged else [n_chunks,nq,k].
     seed_rows: None = automatic (a pre-pass over the first SEED_ROWS rows of large galleries supplies per-query thresholds, which
@@ -105,7 +106,9 @@ def sim_topk(q: torch.Tensor, g: torch.Tensor, k: int = 10, gallery_offset: int 
     maximum of the k-th scores of the chunks of a streamed gallery seen so far); used instead of a pre-pass.  The lists returned then
     hold only candidates that can still enter the union's top-k (possibly fewer than k; the rest is (-inf, INT_MAX)): merge them with
     the lists that produced the threshold.
-    out: (scores fp32, idx int32) buffers of shape [n_chunks, nq, k] for the per-chunk lists (e.g. the two halves of one exchange buffer)."""
+    out: (scores fp32, idx int32) buffers of shape [n_chunks, nq, k] for the per-chunk lists (e.g. the two halves of one exchange buffer).
+    coop: the chunks of the launch share their per-query thresholds through global memory (lpi_sim_topk_coop_bf16): same merged result,
+    fewer sorted insertions; the per-chunk lists may then hold fewer than k entries.  None = automatic (on when n_chunks > 1, dim <= 512)."""
     _lib.require_device()
     _chk(q, torch.bfloat16, "q")
     _chk(g, torch.bfloat16, "g")
@@ -137,8 +140,20 @@ def sim_topk(q: torch.Tensor, g: torch.Tensor, k: int = 10, gallery_offset: int 
     else:
         ps = torch.empty(n_chunks, nq, k, device=q.device, dtype=torch.float32)
         pi = torch.empty(n_chunks, nq, k, device=q.device, dtype=torch.int32)
-    call("sim_topk_bf16", ptr(q), ptr(g), nq, ng, dim, k, C.c_longlong(gallery_offset), n_chunks, thr_ptr, thr_stride, ptr(ps), ptr(pi),
-         stream_ptr())
+    if coop is None:
+        coop = COOP_THRESHOLDS and n_chunks > 1 and dim <= 512
+    if coop:
+        if init_thr is not None:
+            shared = init_thr.clone()
+        elif seed_scores is not None:
+            shared = seed_scores[0, :, k - 1].contiguous()
+        else:
+            shared = torch.full((nq,), float("-inf"), device=q.device, dtype=torch.float32)
+        call("sim_topk_coop_bf16", ptr(q), ptr(g), nq, ng, dim, k, C.c_longlong(gallery_offset), n_chunks, ptr(shared), ptr(ps), ptr(pi),
+             stream_ptr())
+    else:
+        call("sim_topk_bf16", ptr(q), ptr(g), nq, ng, dim, k, C.c_longlong(gallery_offset), n_chunks, thr_ptr, thr_stride, ptr(ps), ptr(pi),
+             stream_ptr())
     _count()
     if not merge:
         return ps, pi

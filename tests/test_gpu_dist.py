@@ -67,6 +67,69 @@ def _train_worker(rank, world, port, out):
         dist.destroy_process_group()
 
 
+def _learner_worker(rank, world, port, out, tmp):
+    """The whole learner data-parallel over 2 ranks: each rank trains on its shard of the task's train set; the K-Means task keys come
+    from the gathered features (identical on every rank), results agree, and rank 0 alone writes the checkpoints / result file."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        from torch.utils.data import DataLoader, Subset
+
+        from lpi_b200 import data as D, synthetic as S
+        from lpi_b200.config import default_args
+        from lpi_b200.sprompt import SPrompts
+
+        os.chdir(tmp)
+        n_tasks = 2
+        args = default_args(clip_state_dict=S.make_clip_state_dict(0), device=[dev], epochs=1, batch_size=4, n_tasks=n_tasks,
+                            group=dist.group.WORLD, checkpoint_dir=os.path.join(tmp, "ckpt"))
+        learner = SPrompts(args)
+        with torch.no_grad():
+            for t in range(n_tasks):
+                for k, v in S.make_prompt_factors(t).items():
+                    getattr(learner._network.prompts[t], k).copy_(v)
+        loaders = []
+        for tr, te in D.make_task_loaders(n_tasks, 16, 6, 2, 8, 8):
+            shard = Subset(tr.dataset, list(range(rank, len(tr.dataset), world)))          # this rank's half of the task's train set
+            loaders.append((DataLoader(shard, batch_size=4, shuffle=False), te))
+        res = learner.incremental_train(loaders)
+        keys = torch.stack(learner.all_keys + learner.textual_all_keys).float()
+        fac = torch.cat([getattr(learner._network.prompts[t], k).detach().reshape(-1) for t in range(n_tasks) for k in S.FACTOR_NAMES])
+        both_k = [torch.empty_like(keys) for _ in range(world)]
+        both_f = [torch.empty_like(fac) for _ in range(world)]
+        dist.all_gather(both_k, keys)
+        dist.all_gather(both_f, fac)
+        all_res = [None] * world
+        dist.all_gather_object(all_res, res)
+        if rank == 0:
+            import glob
+            ok = bool(torch.equal(both_k[0], both_k[1]) and torch.equal(both_f[0], both_f[1]) and all_res[0] == all_res[1])
+            files = sorted(os.listdir(os.path.join(tmp, "ckpt")))
+            ok &= files == ["task_0.pt", "task_1.pt"] and len(glob.glob(os.path.join(tmp, "res", "*.json"))) == 1
+            out.put(("learner", ok, files))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpu_learner_keys_results_and_files(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = 30600 + os.getpid() % 2000
+    procs = [ctx.Process(target=_learner_worker, args=(r, 2, port, out, str(tmp_path))) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = out.get(timeout=900)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert res[1], res
+
+
 @pytest.mark.parametrize("worker", [_scorer_worker, _train_worker])
 def test_two_gpu_parity(worker):
     if torch.cuda.device_count() < 2:

@@ -99,6 +99,62 @@ def test_chained_thresholds_over_gallery_chunks_are_exact():
     assert torch.equal(i, i0) and torch.equal(v, v0)
 
 
+@pytest.mark.parametrize("order", ["random", "ascending", "descending"])
+def test_cooperative_thresholds_are_exact(order):
+    """Chunks of one launch sharing their per-query thresholds through global memory (lpi_sim_topk_coop_bf16) must give exactly the merged
+    lists of the independent chunks -- with exact ties across chunk boundaries and adversarial gallery orders -- while the per-chunk lists
+    themselves may be short.  Repeated launches (timing-dependent sharing) agree with each other."""
+    gen = torch.Generator().manual_seed(29)
+    q = torch.randn(300, 512, generator=gen).bfloat16().cuda()
+    g = torch.randn(60000, 512, generator=gen).bfloat16()
+    g[45000:45040] = g[100:140]                   # ties between the first and the last chunk: the lower index must win
+    g[20000] = g[59999]
+    if order != "random":
+        key = (q[0].float().cpu() @ g.float().t())
+        g = g[torch.argsort(key, descending=(order == "descending"))]
+    g = g.cuda().contiguous()
+    v0, i0 = ops.sim_topk(q, g, 10, 7, 1, seed_rows=0, coop=False)
+    for chunks, seed_rows in ((4, 0), (6, 2048), (3, 16384)):
+        for _ in range(3):
+            ps, pi = ops.sim_topk(q, g, 10, 7, chunks, merge=False, seed_rows=seed_rows, coop=True)
+            v, i = ops.topk_merge(ps, pi)
+            assert torch.equal(i, i0) and torch.equal(v, v0), (order, chunks, seed_rows)
+    assert bool((pi == 0x7FFFFFFF).any())         # some chunk list is short: its candidates were ruled out by another chunk's threshold
+    # init_thr + coop (a streamed gallery whose pieces are themselves chunked)
+    thr = v0[:, 9].contiguous() - 0.25
+    v, i = ops.sim_topk(q, g, 10, 7, 4, init_thr=thr, coop=True)
+    assert torch.equal(i, i0) and torch.equal(v, v0)
+    assert torch.equal(thr, v0[:, 9] - 0.25)      # the caller's tensor is not written
+
+
+def test_fused_merge_recall_equals_separate_kernels():
+    """lpi_topk_merge_recall on an exchange buffer laid out like an all-gather of [2, c, Q, k] per rank == topk_merge + recall_counts."""
+    gen = torch.Generator().manual_seed(31)
+    G, c, nq, k = 3, 2, 777, 10
+    sc = torch.randn(G, c, nq, k, generator=gen).sort(dim=-1, descending=True)[0]
+    sc[1, 0, :, 3] = sc[0, 1, :, 2]               # equal scores in different parts: the lower index must win
+    ix = torch.randperm(G * c * nq * k, generator=gen).to(torch.int32).view(G, c, nq, k) % 5000
+    packed = torch.empty(G, 2, c, nq, k, dtype=torch.int32)
+    packed[:, 0] = sc.view(torch.int32)
+    packed[:, 1] = ix
+    gt = [[int(x) for x in torch.randint(0, 5000, (1 + r % 3,), generator=gen)] for r in range(nq)]
+    for r in range(0, nq, 5):
+        gt[r][0] = int(ix[r % G, r % c, r, r % k])               # plant hits at every position
+    ptr, idx = R.gt_csr(gt)
+    task = (torch.arange(nq) % 4).to(torch.int32)
+    v, i, counts, rank = ops.topk_merge_recall(packed.cuda(), ptr.cuda(), idx.cuda(), task.cuda(), 4, want_rank=True)
+    wv, wi = ops.topk_merge(sc.view(G * c, nq, k).cuda(), ix.view(G * c, nq, k).cuda())
+    wc, wr = ops.recall_counts(wi, ptr.cuda(), idx.cuda(), task.cuda(), 4, want_rank=True)
+    assert torch.equal(v, wv) and torch.equal(i, wi) and torch.equal(counts, wc) and torch.equal(rank, wr)
+    assert int(counts[:, 3].sum()) == nq and int(counts[:, 2].sum()) > 0
+    # single rank, through the helper that owns the buffer layout
+    buf, sv, iv = R.exchange_buffer(c, nq, k, "cuda")
+    sv.copy_(sc[0]); iv.copy_(ix[0])
+    v1, i1, c1 = R.merge_recall(buf, ptr.cuda(), idx.cuda(), task.cuda(), 4)
+    wv1, wi1 = ops.topk_merge(sc[0].cuda(), ix[0].cuda())
+    assert torch.equal(v1, wv1) and torch.equal(i1, wi1) and torch.equal(c1, ops.recall_counts(wi1, ptr.cuda(), idx.cuda(), task.cuda(), 4))
+
+
 def test_topk_rows_and_merge_ties():
     gen = torch.Generator().manual_seed(11)
     s = torch.randn(70, 4001, generator=gen)

@@ -49,6 +49,7 @@ def main():
     ap.add_argument("--batches", default="64,256")
     ap.add_argument("--text-len", type=int, default=77)
     ap.add_argument("--vision-dtype", default="fp16", choices=["fp16", "bf16"])
+    ap.add_argument("--only", default="", help="substring filter on the GEMM name (e.g. dGELU)")
     a = ap.parse_args()
     dev = torch.device("cuda")
     print(f"# {torch.cuda.get_device_name(0)}; ours = lpi_gemm_{{bf16,f16}} with the fused epilogue; cuBLAS = torch.matmul(a, w.t()) same operands, no epilogue")
@@ -56,6 +57,8 @@ def main():
     for B in [int(x) for x in a.batches.split(",")]:
         tot_o = tot_c = tot_f = 0.0
         for tower, name, M, N, K, epi, h in shapes(B, a.text_len, torch.float16 if a.vision_dtype == "fp16" else torch.bfloat16):
+            if a.only and a.only not in name:
+                continue
             g = torch.Generator(device=dev).manual_seed(1)
             x = torch.randn(M, K, device=dev, generator=g).to(h)
             w = (torch.randn(N, K, device=dev, generator=g) * K ** -0.5).to(h)
