@@ -172,6 +172,15 @@ int lpi_im2col_patches_f16(const float* images, void* out_f16, int B, int resolu
 int lpi_assemble_vision(const float* patch_emb, const float* cls, const float* pos, const float* prompt_table, const int* sel,
                         const float* ln_gamma, const float* ln_beta, float* x_out, int B, int n_patch, int P, int D, float eps,
                         void* stream);
+/* The same assembly with the prompt rows reconstructed in the kernel from the DecomposedPrompt factors (prompts.py:38-57 fused with
+ * model.py:240-248: no [L,P,D] table is materialised for the token sequence).  dim1_share [T, n_layers, r], dim2 [T, P, r], dim3 [T, D, r]
+ * for the T selectable tasks (sel[b] picks one; NULL = task 0); layer 0 enters the sequence; bit-identical to lpi_prompt_fwd + assemble. */
+int lpi_assemble_vision_factors(const float* patch_emb, const float* cls, const float* pos, const float* dim1_share, const float* dim2_vis,
+                                const float* dim3_vis, int r, int n_layers, float scale, const int* sel, const float* ln_gamma,
+                                const float* ln_beta, float* x_out, int B, int n_patch, int P, int D, float eps, void* stream);
+int lpi_assemble_vision_factors_bwd(const float* g, const float* dim1_share, const float* dim2_vis, const float* dim3_vis, int r, int n_layers,
+                                    float scale, const int* sel, const float* ln_gamma, float* d_prompt, int B, int L, int P, int n_tables,
+                                    int D, float eps, void* stream);
 int lpi_assemble_vision_bwd(const float* g, const float* prompt_table, const int* sel, const float* ln_gamma, float* d_prompt,
                             int B, int L, int P, int n_tables, int D, float eps, void* stream);
 
@@ -183,6 +192,10 @@ int lpi_assemble_vision_bwd(const float* g, const float* prompt_table, const int
  * ------------------------------------------------------------------------------------------------ */
 int lpi_assemble_text(const float* token_embedding, const long long* tokens, const float* pos, const float* ctx_table,
                       const int* sel, float* x_out, int B, int L, int P, int D, void* stream);
+/* text splice with the context rows reconstructed from the factors (prompts.py:38-57 fused with prompt_learner.py:152-163, 53) */
+int lpi_assemble_text_factors(const float* token_embedding, const long long* tokens, const float* pos, const float* dim1_share,
+                              const float* dim2_txt, const float* dim3_txt, int r, int n_layers, float scale, const int* sel, float* x_out,
+                              int B, int L, int P, int D, void* stream);
 int lpi_assemble_text_bwd(const float* g, const int* sel, float* d_ctx, int B, int L, int P, int n_tables, int D, void* stream);
 /* Opt-in deep-prompt injection (the intended semantics of the dead branch at models/clip/model.py:190-193):
  * x[b, 1+p, :] += prompt[sel[b], p, :] before block `layer`; its backward is lpi_assemble_text_bwd on the block-input gradient. */
@@ -197,6 +210,11 @@ int lpi_inject_prompt_rows(float* x, const float* prompt, const int* sel, int B,
  * ------------------------------------------------------------------------------------------------ */
 int lpi_head_fwd(const float* x, const int* row_idx, const float* ln_gamma, const float* ln_beta, const float* proj, float* z_out,
                  float* feat_out, int B, int D, int E, float eps, void* stream);
+/* head_fwd that also ends in the task-id selection of every sample (sprompt.py:336-368): sel_out[b] = argmin_t min_c |feat[b] - centers[t,c]|_1,
+ * centers [n_tasks, n_centers, E]; the un-prompted pass of the evaluation needs no separate nearest-centre launch. */
+int lpi_head_fwd_select(const float* x, const int* row_idx, const float* ln_gamma, const float* ln_beta, const float* proj, float* z_out,
+                        float* feat_out, const float* centers, int n_tasks, int n_centers, int* sel_out, int B, int D, int E, float eps,
+                        void* stream);
 int lpi_head_bwd(const float* dfeat, const float* dz_direct, const float* z, const float* x, const int* row_idx, const float* ln_gamma,
                  const float* proj, float* g, void* g_bf16, int B, int D, int E, float eps, void* stream);
 /* same with g_f16 = fp16(grad_scale * g) as the shadow (fp16 gradient path, see lpi_layernorm_bwd_f16) */
@@ -225,6 +243,12 @@ int lpi_prompt_bwd(const float* dim1_share, const float* dim2_vis, const float* 
 int lpi_sgemm_f32(const float* A, const float* B, float* C, int M, int N, int K, long long a_m, long long a_k, long long b_k,
                   long long b_n, long long ldc, float alpha, float beta, void* stream);
 int lpi_clip_loss_logits(const float* logits, int n, float weight, float* lse_ws, float* loss_out, float* dlogits, void* stream);
+/* Fused similarity + InfoNCE, forward AND backward, in ONE (cooperative) launch (slinet.py:138-141 + loss.py:75-87 + autograd):
+ * img_f / txt_f [n, E] fp32 L2-normalised features of the GLOBAL batch; loss_out = weight * ClipLoss(scale * I T^T);
+ * d_img / d_txt [n_local, E] = gradients w.r.t. rows [row0, row0 + n_local) of I / T (the rows this rank's towers produced; NULL = skip);
+ * logits_out [n, n] only if non-NULL -- the score matrix is otherwise never written; lse_ws, terms_ws: 2n floats of scratch each. */
+int lpi_sim_infonce_fwd_bwd(const float* img_f, const float* txt_f, int n, int E, float scale, float weight, int row0, int n_local,
+                            float* lse_ws, float* terms_ws, float* loss_out, float* logits_out, float* d_img, float* d_txt, void* stream);
 int lpi_row_mean(const float* x, float* out, int rows, int D, float scale, void* stream);
 int lpi_add_rowconst(float* G, const float* v, long long rows, int D, float alpha, int accumulate, void* stream);
 int lpi_task_loss(const float* X, int R, long long n, const int* target, float temperature, float weight, float* part_ws, int n_part,
@@ -234,6 +258,25 @@ int lpi_sgd_momentum_step(float* w, const float* g, float* v, long long n, float
 /* sel[b] = argmin_t min_c sum_d |f[b,d] - centers[t,c,d]| (methods/sprompt.py:336-368); centers [T,C,E]; sel int64 [B]. */
 int lpi_nearest_center_l1(const float* feats, const float* centers, int B, int n_tasks, int n_centers, int E, long long* sel_out,
                           void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * fp32 parity mode of the towers (north_star: "1e-5 in fp32"; reference = the un-converted fp32 model, clip.py:128-129,
+ * models/clip/model.py:154-196).  Exact fp32 products on the SIMT pipes -- a TEST mode selected with precision="fp32" on the engines:
+ *   linear layers       lpi_sgemm_bias_f32  (C = alpha A B + bias[n] + beta C; arbitrary strides like lpi_sgemm_f32)
+ *   patch extraction    lpi_im2col_patches_f32
+ *   attention           lpi_attn_fwd_f32 / lpi_attn_bwd_f32 on qkv [B*L, 3*H*64] fp32; lse = natural-log sum-exp [B*H*L];
+ *                       delta_ws [B*H*L] scratch; dqkv [B*L, 3*H*64] is overwritten
+ *   QuickGELU           lpi_quick_gelu_f32 / lpi_quick_gelu_bwd_f32 (out = dy * QuickGELU'(z)), model.py:163-165
+ * LayerNorm, token assembly, heads, prompt and loss kernels are fp32 already.
+ * ------------------------------------------------------------------------------------------------ */
+int lpi_sgemm_bias_f32(const float* A, const float* B, const float* bias, float* C, int M, int N, int K, long long a_m, long long a_k,
+                       long long b_k, long long b_n, long long ldc, float alpha, float beta, void* stream);
+int lpi_im2col_patches_f32(const float* images, float* out_f32, int B, int resolution, int patch, void* stream);
+int lpi_attn_fwd_f32(const float* qkv, float* out, float* lse, int B, int L, int H, int causal, void* stream);
+int lpi_attn_bwd_f32(const float* qkv, const float* out, const float* d_out, const float* lse, float* delta_ws, float* dqkv, int B, int L,
+                     int H, int causal, void* stream);
+int lpi_quick_gelu_f32(const float* z, float* out, long long n, void* stream);
+int lpi_quick_gelu_bwd_f32(const float* dy, const float* z, float* out, long long n, void* stream);
 
 #ifdef __cplusplus
 }

@@ -5,6 +5,7 @@
 // retrieval/models/clip/prompt_learner.py:52-63,128-163 (TextEncoder / PromptLearner), retrieval/models/slinet.py:122,133.
 // All rows are [tokens, D] fp32 (residual stream) or bf16 (GEMM operands); one warp per row, 16-byte accesses.
 #include <cuda_fp16.h>
+#include <math_constants.h>
 #include "ptx.cuh"
 #include "lpi_internal.h"
 
@@ -146,6 +147,20 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const float* 
 
 // ------------------------------------------------------------------------------------------------ vision front end
 // images [B,3,R,R] fp32 -> patch rows [B*G*G, 3*P*P] bf16, column = c*P*P + i*P + j (conv1.weight.view(D,-1) order)
+// (fp32 parity mode: the same gather without the 16-bit rounding)
+__global__ void im2col_f32_kernel(const float* __restrict__ img, float* __restrict__ out, int B, int R, int P) {
+    const int G = R / P, K = 3 * P * P;
+    const long n = long(B) * G * G * K / 4;
+    const long t = long(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const long e = t * 4;
+    const int col = int(e % K);
+    const long prow = e / K;
+    const int gx = int(prow % G), gy = int((prow / G) % G), b = int(prow / (G * G));
+    const int c = col / (P * P), i = (col / P) % P, j = col % P;
+    *reinterpret_cast<float4*>(out + e) = *reinterpret_cast<const float4*>(img + ((long(b) * 3 + c) * R + gy * P + i) * R + gx * P + j);
+}
+
 template <bool F16>
 __global__ void im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int R, int P) {
     const int G = R / P, K = 3 * P * P;
@@ -161,14 +176,35 @@ __global__ void im2col_kernel(const float* __restrict__ img, __nv_bfloat16* __re
     *reinterpret_cast<uint2*>(out + e) = make_uint2(pack_h2<F16>(v.x, v.y), pack_h2<F16>(v.z, v.w));
 }
 
+// DecomposedPrompt row straight from the factors (prompts.py:38-57, layer 0): y[c] = scale * (1/r) sum_k (a[k] b[k]) c3[c, k] -- the same
+// association and order as prompt_fwd_kernel, so the fused assembly is bit-identical to reconstruct-then-assemble.
+struct PromptFactors {
+    const float* d1;      // [T, Lp, r] layer factor (dim_1_share) of every selectable task; layer 0 enters the token sequence
+    const float* d2;      // [T, P, r]  prompt factor of this modality
+    const float* d3;      // [T, D, r]  width factor of this modality
+    int r, Lp;
+    float scale;          // DecomposedPrompt.scale (1 in the reference)
+};
+__device__ __forceinline__ float prompt_value(const PromptFactors& f, int t, int p, int P, int D, int c) {
+    const float* a = f.d1 + long(t) * f.Lp * f.r;
+    const float* b = f.d2 + (long(t) * P + p) * f.r;
+    const float* c3 = f.d3 + (long(t) * D + c) * f.r;
+    float s = 0.f;
+    for (int k = 0; k < f.r; ++k) s = fmaf(a[k] * b[k], c3[k], s);
+    s *= 1.f / f.r;
+    return f.scale == 1.f ? s : s * f.scale;
+}
+
 // Token assembly + ln_pre (model.py:235-250).  Row l of sample b:
 //   l = 0          : class_embedding + pos[0]
 //   1 <= l <= P    : prompt_table[sel[b]][l-1]              (NO positional term)
 //   l > P          : patch_emb[b, l-1-P] + pos[l-P]
+//   (prompt rows: from the materialised table, or -- fac.d1 != nullptr -- reconstructed here from the tri-factor decomposition)
 template <int NV>
 __global__ void assemble_vision_kernel(const float* __restrict__ patch_emb, const float* __restrict__ cls, const float* __restrict__ pos,
                                        const float* __restrict__ prompt_table, const int* __restrict__ sel, const float* __restrict__ gamma,
-                                       const float* __restrict__ beta, float* __restrict__ x_out, int B, int n_patch, int P, int D, float eps) {
+                                       const float* __restrict__ beta, float* __restrict__ x_out, int B, int n_patch, int P, int D, float eps,
+                                       PromptFactors fac) {
     const int L = 1 + P + n_patch;
     const long row = (long(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     if (row >= long(B) * L) return;
@@ -183,7 +219,9 @@ __global__ void assemble_vision_kernel(const float* __restrict__ patch_emb, cons
             v[i] = make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w);
         } else if (l <= P) {
             const int t = sel ? sel[b] : 0;
-            v[i] = *reinterpret_cast<const float4*>(prompt_table + (long(t) * P + (l - 1)) * D + c);
+            if (fac.d1) v[i] = make_float4(prompt_value(fac, t, l - 1, P, D, c), prompt_value(fac, t, l - 1, P, D, c + 1),
+                                           prompt_value(fac, t, l - 1, P, D, c + 2), prompt_value(fac, t, l - 1, P, D, c + 3));
+            else v[i] = *reinterpret_cast<const float4*>(prompt_table + (long(t) * P + (l - 1)) * D + c);
         } else {
             const float4 a = *reinterpret_cast<const float4*>(patch_emb + (long(b) * n_patch + (l - 1 - P)) * D + c);
             const float4 p = *reinterpret_cast<const float4*>(pos + long(l - P) * D + c);
@@ -197,15 +235,20 @@ __global__ void assemble_vision_kernel(const float* __restrict__ patch_emb, cons
 // d prompt_table[t, p, :] = sum over {b : sel[b] == t} of LNbwd(g[b, 1+p, :]; x = prompt_table[t, p, :])
 // grid = (P, T); each warp walks a strided slice of the batch, block-level reduction in shared memory (deterministic).
 template <int NV>
-__global__ void assemble_vision_bwd_kernel(const float* __restrict__ g, const float* __restrict__ prompt_table, const int* __restrict__ sel,
-                                           const float* __restrict__ gamma, float* __restrict__ d_prompt, int B, int L, int P, int D, float eps) {
+__global__ void __launch_bounds__(512)
+assemble_vision_bwd_kernel(const float* __restrict__ g, const float* __restrict__ prompt_table, const int* __restrict__ sel,
+                                           const float* __restrict__ gamma, float* __restrict__ d_prompt, int B, int L, int P, int D, float eps,
+                                           PromptFactors fac) {
     extern __shared__ float red[];                   // [warps][D]
     const int p = blockIdx.x, t = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     float4 xv[NV], acc[NV];
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-        xv[i] = *reinterpret_cast<const float4*>(prompt_table + (long(t) * P + p) * D + (i * 32 + lane) * 4);
+        const int c = (i * 32 + lane) * 4;
+        if (fac.d1) xv[i] = make_float4(prompt_value(fac, t, p, P, D, c), prompt_value(fac, t, p, P, D, c + 1), prompt_value(fac, t, p, P, D, c + 2),
+                                        prompt_value(fac, t, p, P, D, c + 3));
+        else xv[i] = *reinterpret_cast<const float4*>(prompt_table + (long(t) * P + p) * D + c);
         acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     for (int b = warp; b < B; b += nw) {
@@ -232,11 +275,21 @@ __global__ void assemble_vision_bwd_kernel(const float* __restrict__ g, const fl
 // x[b, l] = (l in [1, P] and ctx given ? ctx_table[sel[b]][l-1] : token_embedding[tok[b, l]]) + pos[l]
 __global__ void assemble_text_kernel(const float* __restrict__ emb, const long long* __restrict__ tok, const float* __restrict__ pos,
                                      const float* __restrict__ ctx_table, const int* __restrict__ sel, float* __restrict__ x_out, int B, int L,
-                                     int P, int D) {
+                                     int P, int D, PromptFactors fac) {
     const long row = (long(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     if (row >= long(B) * L) return;
     const int lane = threadIdx.x & 31;
     const int b = int(row / L), l = int(row % L);
+    if (fac.d1 && l >= 1 && l <= P) {                // context row reconstructed from the factors (+ positional term, prompt_learner.py:53)
+        const int t = sel ? sel[b] : 0;
+        for (int c = lane * 4; c < D; c += 128) {
+            const float4 p = *reinterpret_cast<const float4*>(pos + long(l) * D + c);
+            *reinterpret_cast<float4*>(x_out + row * D + c) =
+                make_float4(prompt_value(fac, t, l - 1, P, D, c) + p.x, prompt_value(fac, t, l - 1, P, D, c + 1) + p.y,
+                            prompt_value(fac, t, l - 1, P, D, c + 2) + p.z, prompt_value(fac, t, l - 1, P, D, c + 3) + p.w);
+        }
+        return;
+    }
     const float* src;
     if (ctx_table && l >= 1 && l <= P) src = ctx_table + (long(sel ? sel[b] : 0) * P + (l - 1)) * D;
     else src = emb + long(tok[row]) * D;
@@ -341,6 +394,33 @@ __global__ void head_norm_kernel(const float* __restrict__ z, float* __restrict_
     for (int e = lane; e < E; e += 32) { const float v = z[long(b) * E + e]; ss += v * v; }
     const float inv = 1.f / sqrtf(warp_sum(ss));
     for (int e = lane; e < E; e += 32) feat[long(b) * E + e] = z[long(b) * E + e] * inv;
+}
+
+// feat[b] = z[b] / ||z[b]|| AND the task-id of sample b in the same warp (sprompt.py:336-368: argmin over tasks of the min L1 distance to
+// the task's centres, first occurrence on ties) -- the un-prompted pass of the evaluation ends in its selection, no extra launch.
+// Same summation order as nearest_center_kernel (loss.cu), so the selection is bit-identical to the two-kernel form.
+__global__ void head_norm_select_kernel(const float* __restrict__ z, float* __restrict__ feat, const float* __restrict__ centers, int T, int C,
+                                        int* __restrict__ sel, int B, int E) {
+    const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (b >= B) return;
+    float ss = 0.f;
+    for (int e = lane; e < E; e += 32) { const float v = z[long(b) * E + e]; ss += v * v; }
+    const float inv = 1.f / sqrtf(warp_sum(ss));
+    for (int e = lane; e < E; e += 32) feat[long(b) * E + e] = z[long(b) * E + e] * inv;
+    float best = CUDART_INF_F;
+    int best_t = 0;
+    for (int t = 0; t < T; ++t) {
+        float tmin = CUDART_INF_F;
+        for (int c = 0; c < C; ++c) {
+            const float* k = centers + (long(t) * C + c) * E;
+            float s = 0.f;
+            for (int d = lane; d < E; d += 32) s += fabsf(z[long(b) * E + d] * inv - k[d]);
+            s = warp_sum(s);
+            tmin = fminf(tmin, s);
+        }
+        if (tmin < best) { best = tmin; best_t = t; }
+    }
+    if (lane == 0) sel[b] = best_t;
 }
 
 // Backward of the head in two kernels (the first version ran everything for one sample in one block: 64 blocks, each streaming
@@ -517,45 +597,104 @@ extern "C" int lpi_im2col_patches(const float* images, void* out_bf16, int B, in
     return im2col_entry(images, out_bf16, false, B, resolution, patch, stream);
 }
 
+extern "C" int lpi_im2col_patches_f32(const float* images, float* out_f32, int B, int resolution, int patch, void* stream) {
+    if (B <= 0) return LPI_OK;
+    if (patch % 4 || resolution % patch) return set_error(LPI_ERR_ARG, "im2col: bad resolution %d / patch %d", resolution, patch);
+    const int G = resolution / patch;
+    const long n = long(B) * G * G * 3 * patch * patch / 4;
+    im2col_f32_kernel<<<unsigned((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(images, out_f32, B, resolution, patch);
+    return check_launch("im2col_f32");
+}
+
 extern "C" int lpi_im2col_patches_f16(const float* images, void* out_f16, int B, int resolution, int patch, void* stream) {
     return im2col_entry(images, out_f16, true, B, resolution, patch, stream);
 }
 
-extern "C" int lpi_assemble_vision(const float* patch_emb, const float* cls, const float* pos, const float* prompt_table, const int* sel,
-                                   const float* ln_gamma, const float* ln_beta, float* x_out, int B, int n_patch, int P, int D, float eps,
-                                   void* stream) {
+static int assemble_vision_impl(const float* patch_emb, const float* cls, const float* pos, const float* prompt_table, PromptFactors fac,
+                                const int* sel, const float* ln_gamma, const float* ln_beta, float* x_out, int B, int n_patch, int P, int D,
+                                float eps, void* stream) {
     if (B <= 0) return LPI_OK;
-    if (P > 0 && !prompt_table) return set_error(LPI_ERR_ARG, "assemble_vision: P=%d but no prompt table", P);
+    if (P > 0 && !prompt_table && !fac.d1) return set_error(LPI_ERR_ARG, "assemble_vision: P=%d but neither a prompt table nor factors", P);
     const long rows = long(B) * (1 + P + n_patch);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int rc = dispatch_nv(D, [&](auto nv) {
         assemble_vision_kernel<decltype(nv)::value><<<warp_grid(rows, 256), 256, 0, st>>>(patch_emb, cls, pos, prompt_table, sel, ln_gamma,
-                                                                                            ln_beta, x_out, B, n_patch, P, D, eps);
+                                                                                            ln_beta, x_out, B, n_patch, P, D, eps, fac);
         return 0;
     });
     return rc ? rc : check_launch("assemble_vision");
 }
 
-extern "C" int lpi_assemble_vision_bwd(const float* g, const float* prompt_table, const int* sel, const float* ln_gamma, float* d_prompt,
-                                       int B, int L, int P, int n_tables, int D, float eps, void* stream) {
+static int check_factors(const float* d1, const float* d2, const float* d3, int r, int Lp, const char* what) {
+    if (!d1 || !d2 || !d3) return set_error(LPI_ERR_ARG, "%s: null factor", what);
+    if (r < 1 || r > 8 || Lp < 1) return set_error(LPI_ERR_ARG, "%s: bad rank r=%d / layer count %d", what, r, Lp);
+    return LPI_OK;
+}
+
+extern "C" int lpi_assemble_vision(const float* patch_emb, const float* cls, const float* pos, const float* prompt_table, const int* sel,
+                                   const float* ln_gamma, const float* ln_beta, float* x_out, int B, int n_patch, int P, int D, float eps,
+                                   void* stream) {
+    return assemble_vision_impl(patch_emb, cls, pos, prompt_table, PromptFactors{nullptr, nullptr, nullptr, 0, 0, 1.f}, sel, ln_gamma, ln_beta,
+                                x_out, B, n_patch, P, D, eps, stream);
+}
+
+extern "C" int lpi_assemble_vision_factors(const float* patch_emb, const float* cls, const float* pos, const float* dim1_share,
+                                           const float* dim2_vis, const float* dim3_vis, int r, int n_layers, float scale, const int* sel,
+                                           const float* ln_gamma, const float* ln_beta, float* x_out, int B, int n_patch, int P, int D,
+                                           float eps, void* stream) {
+    if (int rc = check_factors(dim1_share, dim2_vis, dim3_vis, r, n_layers, "assemble_vision_factors")) return rc;
+    return assemble_vision_impl(patch_emb, cls, pos, nullptr, PromptFactors{dim1_share, dim2_vis, dim3_vis, r, n_layers, scale}, sel, ln_gamma,
+                                ln_beta, x_out, B, n_patch, P, D, eps, stream);
+}
+
+static int assemble_vision_bwd_impl(const float* g, const float* prompt_table, PromptFactors fac, const int* sel, const float* ln_gamma,
+                                    float* d_prompt, int B, int L, int P, int n_tables, int D, float eps, void* stream) {
     if (B <= 0 || P <= 0) return LPI_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int threads = 512;
     int rc = dispatch_nv(D, [&](auto nv) {
         assemble_vision_bwd_kernel<decltype(nv)::value><<<dim3(P, n_tables), threads, (threads / 32) * D * sizeof(float), st>>>(
-            g, prompt_table, sel, ln_gamma, d_prompt, B, L, P, D, eps);
+            g, prompt_table, sel, ln_gamma, d_prompt, B, L, P, D, eps, fac);
         return 0;
     });
     return rc ? rc : check_launch("assemble_vision_bwd");
 }
 
-extern "C" int lpi_assemble_text(const float* token_embedding, const long long* tokens, const float* pos, const float* ctx_table,
-                                 const int* sel, float* x_out, int B, int L, int P, int D, void* stream) {
+extern "C" int lpi_assemble_vision_bwd(const float* g, const float* prompt_table, const int* sel, const float* ln_gamma, float* d_prompt,
+                                       int B, int L, int P, int n_tables, int D, float eps, void* stream) {
+    return assemble_vision_bwd_impl(g, prompt_table, PromptFactors{nullptr, nullptr, nullptr, 0, 0, 1.f}, sel, ln_gamma, d_prompt, B, L, P,
+                                    n_tables, D, eps, stream);
+}
+
+extern "C" int lpi_assemble_vision_factors_bwd(const float* g, const float* dim1_share, const float* dim2_vis, const float* dim3_vis, int r,
+                                               int n_layers, float scale, const int* sel, const float* ln_gamma, float* d_prompt, int B, int L,
+                                               int P, int n_tables, int D, float eps, void* stream) {
+    if (int rc = check_factors(dim1_share, dim2_vis, dim3_vis, r, n_layers, "assemble_vision_factors_bwd")) return rc;
+    return assemble_vision_bwd_impl(g, nullptr, PromptFactors{dim1_share, dim2_vis, dim3_vis, r, n_layers, scale}, sel, ln_gamma, d_prompt, B,
+                                    L, P, n_tables, D, eps, stream);
+}
+
+static int assemble_text_impl(const float* token_embedding, const long long* tokens, const float* pos, const float* ctx_table,
+                              PromptFactors fac, const int* sel, float* x_out, int B, int L, int P, int D, void* stream) {
     if (B <= 0) return LPI_OK;
     if (D % 128) return set_error(LPI_ERR_ARG, "assemble_text: D=%d must be a multiple of 128", D);
     assemble_text_kernel<<<warp_grid(long(B) * L, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(token_embedding, tokens, pos, ctx_table,
-                                                                                                      sel, x_out, B, L, P, D);
+                                                                                                      sel, x_out, B, L, P, D, fac);
     return check_launch("assemble_text");
+}
+
+extern "C" int lpi_assemble_text(const float* token_embedding, const long long* tokens, const float* pos, const float* ctx_table,
+                                 const int* sel, float* x_out, int B, int L, int P, int D, void* stream) {
+    return assemble_text_impl(token_embedding, tokens, pos, ctx_table, PromptFactors{nullptr, nullptr, nullptr, 0, 0, 1.f}, sel, x_out, B, L, P,
+                              D, stream);
+}
+
+extern "C" int lpi_assemble_text_factors(const float* token_embedding, const long long* tokens, const float* pos, const float* dim1_share,
+                                         const float* dim2_txt, const float* dim3_txt, int r, int n_layers, float scale, const int* sel,
+                                         float* x_out, int B, int L, int P, int D, void* stream) {
+    if (int rc = check_factors(dim1_share, dim2_txt, dim3_txt, r, n_layers, "assemble_text_factors")) return rc;
+    return assemble_text_impl(token_embedding, tokens, pos, nullptr, PromptFactors{dim1_share, dim2_txt, dim3_txt, r, n_layers, scale}, sel,
+                              x_out, B, L, P, D, stream);
 }
 
 extern "C" int lpi_assemble_text_bwd(const float* g, const int* sel, float* d_ctx, int B, int L, int P, int n_tables, int D, void* stream) {
@@ -582,6 +721,20 @@ extern "C" int lpi_head_fwd(const float* x, const int* row_idx, const float* ln_
     head_fwd_kernel<<<dim3((B + HB - 1) / HB, (E + 31) / 32), 256, smem, st>>>(x, row_idx, ln_gamma, ln_beta, proj, z_out, B, D, E, eps);
     head_norm_kernel<<<(B * 32 + 255) / 256, 256, 0, st>>>(z_out, feat_out, B, E);
     return check_launch("head_fwd");
+}
+
+extern "C" int lpi_head_fwd_select(const float* x, const int* row_idx, const float* ln_gamma, const float* ln_beta, const float* proj,
+                                   float* z_out, float* feat_out, const float* centers, int n_tasks, int n_centers, int* sel_out, int B, int D,
+                                   int E, float eps, void* stream) {
+    if (B <= 0) return LPI_OK;
+    if (D % 64) return set_error(LPI_ERR_ARG, "head_fwd_select: D=%d must be a multiple of 64", D);
+    if (!centers || !sel_out || n_tasks < 1 || n_centers < 1) return set_error(LPI_ERR_ARG, "head_fwd_select: no centres / selection buffer");
+    const int smem = (HB * D + 8 * HB * 32) * sizeof(float);
+    if (smem > 48 * 1024) return set_error(LPI_ERR_UNSUPPORTED, "head_fwd_select: D=%d too wide", D);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    head_fwd_kernel<<<dim3((B + HB - 1) / HB, (E + 31) / 32), 256, smem, st>>>(x, row_idx, ln_gamma, ln_beta, proj, z_out, B, D, E, eps);
+    head_norm_select_kernel<<<(B * 32 + 255) / 256, 256, 0, st>>>(z_out, feat_out, centers, n_tasks, n_centers, sel_out, B, E);
+    return check_launch("head_fwd_select");
 }
 
 static int head_bwd_impl(const float* dfeat, const float* dz_direct, const float* z, const float* x, const int* row_idx, const float* ln_gamma,

@@ -7,6 +7,7 @@
 #include "ptx.cuh"
 #include "lpi_internal.h"
 #include <math_constants.h>
+#include <cooperative_groups.h>
 
 namespace lpi {
 
@@ -14,7 +15,7 @@ namespace lpi {
 // C[m,n] = alpha * sum_k A[m*a_m + k*a_k] * B[k*b_k + n*b_n] (+ beta * C[m,n]);  64x64 tile, 16-deep, 256 threads x (4x4)
 __global__ void __launch_bounds__(256)
 sgemm_kernel(const float* __restrict__ A, const float* __restrict__ Bm, float* __restrict__ C, int M, int N, int K, long a_m, long a_k,
-             long b_k, long b_n, long ldc, float alpha, float beta) {
+             long b_k, long b_n, long ldc, float alpha, float beta, const float* __restrict__ bias = nullptr) {
     __shared__ float sA[16][64 + 4];
     __shared__ float sB[16][64 + 4];
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -51,6 +52,7 @@ sgemm_kernel(const float* __restrict__ A, const float* __restrict__ Bm, float* _
             const int gm = m0 + ty * 4 + i, gn = n0 + tx * 4 + j;
             if (gm < M && gn < N) {
                 float v = alpha * acc[i][j];
+                if (bias) v += bias[gn];
                 if (beta != 0.f) v += beta * C[gm * ldc + gn];
                 C[gm * ldc + gn] = v;
             }
@@ -105,6 +107,102 @@ __global__ void clip_dlogits_kernel(const float* __restrict__ S, const float* __
     float g = expf(s - lse[i]) + expf(s - lse[n + j]);
     if (i == j) g -= 2.f;
     dS[e] = weight * g / (2.f * n);
+}
+
+// ------------------------------------------------------------------------------------------------ fused similarity + InfoNCE, forward and backward
+// north_star subsystem 3 (reference: logits = exp(logit_scale) * I @ T^T, slinet.py:138-141; ClipLoss.forward, loss.py:75-87; autograd):
+// ONE cooperative launch computes the n x n scaled similarities, both log-sum-exps, the loss and the gradients of the local feature rows
+//     dI[i] = scale * sum_j G[i,j] T[j],  dT[j] = scale * sum_i G[i,j] I[i],   G = weight * (softmax_row + softmax_col - 2 Id) / (2n)
+// without the logits ever having to exist in memory (they are written only when the caller asks for them).  One warp owns one row of I
+// (or of T): its feature row sits in registers, the lanes split the width, every score is one warp-reduced fp32 dot product (exact fp32
+// products: the loss path keeps no tensor-core rounding), recomputed in the backward phase instead of stored.  Phases are separated by
+// grid-wide barriers; all reductions run in a fixed order (deterministic).  Work: ~5 n^2 E MACs -- microseconds at the global batches of
+// BASELINE configs[2] (64 ... 512), a few ms at n = 4096.
+namespace cg = cooperative_groups;
+
+template <int NV>          // feature width E = 32 * NV' with NV' <= NV
+__global__ void __launch_bounds__(256)
+sim_infonce_kernel(const float* __restrict__ img, const float* __restrict__ txt, int n, int E, float scale, float weight, int row0, int n_local,
+                   float* __restrict__ lse, float* __restrict__ terms, float* __restrict__ loss, float* __restrict__ logits,
+                   float* __restrict__ d_img, float* __restrict__ d_txt) {
+    cg::grid_group grid = cg::this_grid();
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int nv = E >> 5;
+    // ---- phase 1: row log-sum-exps (tasks [0, n): rows of I against all of T) and column ones (tasks [n, 2n): rows of T against all of I)
+    for (int task = gw; task < 2 * n; task += nwarps) {
+        const bool col = task >= n;
+        const int idx = col ? task - n : task;
+        const float* A = (col ? txt : img) + size_t(idx) * E;
+        const float* Bm = col ? img : txt;
+        float a[NV];
+#pragma unroll
+        for (int t = 0; t < NV; ++t) a[t] = t < nv ? A[lane + 32 * t] : 0.f;
+        float m = -CUDART_INF_F, l = 0.f, diag = 0.f;
+        for (int j = 0; j < n; ++j) {
+            const float* b = Bm + size_t(j) * E;
+            float p = 0.f;
+#pragma unroll
+            for (int t = 0; t < NV; ++t) if (t < nv) p = fmaf(a[t], b[lane + 32 * t], p);
+            const float sc = scale * warp_sum(p);
+            const float mn = fmaxf(m, sc);
+            l = l * expf(m - mn) + expf(sc - mn);
+            m = mn;
+            if (j == idx) diag = sc;
+            if (!col && logits && lane == 0) logits[size_t(idx) * n + j] = sc;
+        }
+        if (lane == 0) {
+            const float v = m + logf(l);
+            lse[task] = v;
+            terms[task] = v - diag;
+        }
+    }
+    grid.sync();
+    // ---- phase 2: loss = weight / (2n) * sum_i [(row_lse_i - S_ii) + (col_lse_i - S_ii)], one block, fixed order
+    if (blockIdx.x == 0) {
+        __shared__ float red[8];
+        float s = 0.f;
+        for (int i = threadIdx.x; i < 2 * n; i += blockDim.x) s += terms[i];
+        s = warp_sum(s);
+        if (lane == 0) red[threadIdx.x >> 5] = s;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float v = 0.f;
+            for (int w = 0; w < (blockDim.x >> 5); ++w) v += red[w];
+            *loss = weight * v / (2.f * n);
+        }
+    }
+    // ---- phase 3: gradients of the local rows (tasks [0, n_local): dI rows; [n_local, 2 n_local): dT rows); scores are recomputed
+    if (d_img == nullptr && d_txt == nullptr) return;
+    const float w2 = weight / (2.f * n);
+    for (int task = gw; task < 2 * n_local; task += nwarps) {
+        const bool col = task >= n_local;
+        const int idx = row0 + (col ? task - n_local : task);
+        float* out = col ? d_txt : d_img;
+        if (!out) continue;
+        const float* A = (col ? txt : img) + size_t(idx) * E;
+        const float* Bm = col ? img : txt;
+        const float own = lse[col ? n + idx : idx];              // LSE of this row (row side) / column (column side)
+        const float* other = col ? lse : lse + n;                // LSEs of the opposite side, indexed by j
+        float a[NV], acc[NV];
+#pragma unroll
+        for (int t = 0; t < NV; ++t) { a[t] = t < nv ? A[lane + 32 * t] : 0.f; acc[t] = 0.f; }
+        for (int j = 0; j < n; ++j) {
+            const float* b = Bm + size_t(j) * E;
+            float bv[NV], p = 0.f;
+#pragma unroll
+            for (int t = 0; t < NV; ++t) { bv[t] = t < nv ? b[lane + 32 * t] : 0.f; p = fmaf(a[t], bv[t], p); }
+            const float sc = scale * warp_sum(p);
+            float g = expf(sc - own) + expf(sc - other[j]);
+            if (j == idx) g -= 2.f;
+            g *= w2;
+#pragma unroll
+            for (int t = 0; t < NV; ++t) acc[t] = fmaf(g, bv[t], acc[t]);
+        }
+        float* o = out + size_t(col ? task - n_local : task) * E;
+#pragma unroll
+        for (int t = 0; t < NV; ++t) if (t < nv) o[lane + 32 * t] = scale * acc[t];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ prompt-side helpers
@@ -257,6 +355,15 @@ extern "C" int lpi_sgemm_f32(const float* A, const float* B, float* C, int M, in
     return check_launch("sgemm_f32");
 }
 
+// C = alpha * A @ B + bias[n] + beta * C: the linear layers of the fp32 parity mode of the towers (exact fp32 products, FFMA)
+extern "C" int lpi_sgemm_bias_f32(const float* A, const float* B, const float* bias, float* C, int M, int N, int K, long long a_m,
+                                  long long a_k, long long b_k, long long b_n, long long ldc, float alpha, float beta, void* stream) {
+    if (M <= 0 || N <= 0) return LPI_OK;
+    sgemm_kernel<<<dim3((N + 63) / 64, (M + 63) / 64), 256, 0, static_cast<cudaStream_t>(stream)>>>(A, B, C, M, N, K, a_m, a_k, b_k, b_n, ldc,
+                                                                                                     alpha, beta, bias);
+    return check_launch("sgemm_bias_f32");
+}
+
 extern "C" int lpi_clip_loss_logits(const float* logits, int n, float weight, float* lse_ws /* 2n */, float* loss_out, float* dlogits,
                                     void* stream) {
     if (n <= 0) return set_error(LPI_ERR_ARG, "clip_loss: empty logits");
@@ -268,6 +375,34 @@ extern "C" int lpi_clip_loss_logits(const float* logits, int n, float weight, fl
         clip_dlogits_kernel<<<unsigned((ne + 255) / 256), 256, 0, st>>>(logits, lse_ws, n, dlogits, weight);
     }
     return check_launch("clip_loss_logits");
+}
+
+extern "C" int lpi_sim_infonce_fwd_bwd(const float* img_f, const float* txt_f, int n, int E, float scale, float weight, int row0, int n_local,
+                                       float* lse_ws /* 2n */, float* terms_ws /* 2n */, float* loss_out, float* logits_out /* n*n or NULL */,
+                                       float* d_img /* [n_local, E] or NULL */, float* d_txt /* [n_local, E] or NULL */, void* stream) {
+    if (n <= 0) return set_error(LPI_ERR_ARG, "sim_infonce: empty batch");
+    if (E % 32 || E < 32 || E > 1024) return set_error(LPI_ERR_ARG, "sim_infonce: E=%d must be a multiple of 32 in [32, 1024]", E);
+    if (row0 < 0 || n_local < 0 || row0 + n_local > n) return set_error(LPI_ERR_ARG, "sim_infonce: local rows [%d, %d) outside [0, %d)", row0, row0 + n_local, n);
+    if (!lse_ws || !terms_ws || !loss_out) return set_error(LPI_ERR_ARG, "sim_infonce: workspace / loss pointer missing");
+    auto kern = (E <= 512) ? sim_infonce_kernel<16> : sim_infonce_kernel<32>;
+    static int max_blocks[2] = {0, 0};
+    const int slot = E <= 512 ? 0 : 1;
+    if (!max_blocks[slot]) {
+        int per_sm = 0, dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0) != cudaSuccess || per_sm < 1)
+            return set_error(LPI_ERR_CUDA, "sim_infonce: occupancy query failed");
+        max_blocks[slot] = per_sm * sms;                         // a cooperative grid must be co-resident
+    }
+    const long warps = 2L * n;
+    int grid = int((warps + 7) / 8);
+    if (grid > max_blocks[slot]) grid = max_blocks[slot];
+    if (grid < 1) grid = 1;
+    void* args[] = {&img_f, &txt_f, &n, &E, &scale, &weight, &row0, &n_local, &lse_ws, &terms_ws, &loss_out, &logits_out, &d_img, &d_txt};
+    cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kern), dim3(grid), dim3(256), args, 0, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return set_error(LPI_ERR_CUDA, "sim_infonce: cooperative launch: %s", cudaGetErrorString(e));
+    return LPI_OK;
 }
 
 extern "C" int lpi_row_mean(const float* x, float* out, int rows, int D, float scale, void* stream) {

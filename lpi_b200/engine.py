@@ -100,9 +100,12 @@ class Tower:
     """12 pre-LN residual attention blocks (model.py:187-196) over a [B*L, D] fp32 residual stream."""
 
     def __init__(self, sd, prefix: str, heads: int, causal: bool, dev, need_grad: bool = True, precision: str = "bf16"):
-        if precision not in ("bf16", "tf32", "fp16"):
-            raise ValueError(f"precision must be 'bf16', 'fp16' or 'tf32', got {precision!r}")
-        self.tf32 = precision == "tf32"
+        if precision not in ("bf16", "tf32", "fp16", "fp32"):
+            raise ValueError(f"precision must be 'bf16', 'fp16', 'tf32' or 'fp32', got {precision!r}")
+        # 'fp32' = the parity mode of north_star ("1e-5 in fp32"): the same block sequence as 'tf32' (fp32 tensors everywhere) with exact
+        # fp32 products on the SIMT pipes (ops.gemm_f32) and fp32 attention (ops.attn_fwd_f32 / attn_bwd_f32) -- a test mode
+        self.fp32 = precision == "fp32"
+        self.tf32 = precision in ("tf32", "fp32")
         self.half = torch.float16 if precision == "fp16" else torch.bfloat16      # dtype of GEMM / attention operands and shadows
         # fp16 gradient path: the 16-bit gradient stream is carried times 2^10 so that small gradients stay in fp16's normal range
         # (min normal 6.1e-5); every op between two LayerNorm backwards is linear in the gradient, so the factor is exact.
@@ -150,19 +153,25 @@ class Tower:
 
     def _forward_tf32(self, x, B, L, tape, inject):
         """Same block sequence with fp32 GEMM operands on the TF32 tensor-core path (8x finer operand rounding than bf16);
-        attention still runs on bf16 q/k/v but hands its output over in fp32."""
+        attention still runs on bf16 q/k/v but hands its output over in fp32.  precision 'fp32': exact-fp32 SIMT GEMMs and attention."""
         H = self.heads
+        mm = ops.gemm_f32 if self.fp32 else ops.gemm_tf32
         for li, w in enumerate(self.blocks):
             if inject is not None and li != 0 and li in inject["layers"]:
                 ops.inject_prompt_rows(x, inject["table"][:, li].contiguous(), inject["sel"], B, L, inject["P"], self.width)
             h, _ = ops.layernorm_fwd(x, w.ln1_g, w.ln1_b, want_f32=True, want_bf16=False)
-            qkv = ops.gemm_tf32(h, w.w_in, ops.EPI_BIAS_BF16, bias=w.b_in)
-            o, lse, of = ops.attn_fwd(qkv, B, L, H, self.causal, want_lse=tape is not None, want_f32=True)
-            x1 = ops.gemm_tf32(of, w.w_out, ops.EPI_BIAS_RESID_F32, bias=w.b_out, resid=x, out=None if tape is not None else x)
+            if self.fp32:
+                qkv = mm(h, w.w_in, ops.EPI_BIAS_F32, bias=w.b_in)
+                of, lse = ops.attn_fwd_f32(qkv, B, L, H, self.causal)
+                o = of
+            else:
+                qkv = mm(h, w.w_in, ops.EPI_BIAS_BF16, bias=w.b_in)
+                o, lse, of = ops.attn_fwd(qkv, B, L, H, self.causal, want_lse=tape is not None, want_f32=True)
+            x1 = mm(of, w.w_out, ops.EPI_BIAS_RESID_F32, bias=w.b_out, resid=x, out=None if tape is not None else x)
             h2, _ = ops.layernorm_fwd(x1, w.ln2_g, w.ln2_b, want_f32=True, want_bf16=False)
             z = torch.empty(x.shape[0], 4 * self.width, device=x.device, dtype=torch.float32) if tape is not None else None
-            a = ops.gemm_tf32(h2, w.w_fc, ops.EPI_BIAS_GELU_F32, bias=w.b_fc, out2=z)
-            x2 = ops.gemm_tf32(a, w.w_proj, ops.EPI_BIAS_RESID_F32, bias=w.b_proj, resid=x1, out=None if tape is not None else x1)
+            a = mm(h2, w.w_fc, ops.EPI_BIAS_GELU_F32, bias=w.b_fc, out2=z)
+            x2 = mm(a, w.w_proj, ops.EPI_BIAS_RESID_F32, bias=w.b_proj, resid=x1, out=None if tape is not None else x1)
             if tape is not None:
                 tape.blocks.append(BlockSaved(x=x, x1=x1, qkv=qkv, o=o, lse=lse, z=z))
             x = x2
@@ -172,14 +181,19 @@ class Tower:
 
     def _backward_tf32(self, tape, g, inject, inject_grads):
         B, L, H = tape.B, tape.L, self.heads
+        mm = ops.gemm_f32 if self.fp32 else ops.gemm_tf32
         for li in range(len(self.blocks) - 1, -1, -1):
             w, s = self.blocks[li], tape.blocks[li]
-            dz = ops.gemm_tf32(g, w.w_proj_t, ops.EPI_DGELU_F32, aux=s.z)
-            dh2 = ops.gemm_tf32(dz, w.w_fc_t, ops.EPI_F32)
+            dz = mm(g, w.w_proj_t, ops.EPI_DGELU_F32, aux=s.z)
+            dh2 = mm(dz, w.w_fc_t, ops.EPI_F32)
             ops.layernorm_bwd(dh2, s.x1, w.ln2_g, g, None, accumulate=True)
-            do = ops.gemm_tf32(g, w.w_out_t, ops.EPI_BF16)
-            dqkv = ops.attn_bwd(s.qkv, s.o, do, s.lse, B, L, H, self.causal, f32=True)
-            dh1 = ops.gemm_tf32(dqkv, w.w_in_t, ops.EPI_F32)
+            if self.fp32:
+                do = mm(g, w.w_out_t, ops.EPI_F32)
+                dqkv = ops.attn_bwd_f32(s.qkv, s.o, do, s.lse, B, L, H, self.causal)
+            else:
+                do = mm(g, w.w_out_t, ops.EPI_BF16)
+                dqkv = ops.attn_bwd(s.qkv, s.o, do, s.lse, B, L, H, self.causal, f32=True)
+            dh1 = mm(dqkv, w.w_in_t, ops.EPI_F32)
             ops.layernorm_bwd(dh1, s.x, w.ln1_g, g, None, accumulate=True)
             if inject is not None and li != 0 and li in inject["layers"] and inject_grads is not None:
                 inject_grads[li] = ops.sum_prompt_rows(g, inject["sel"], B, L, inject["P"], inject["table"].shape[0], self.width)
@@ -225,10 +239,10 @@ class VisionEngine:
         import os
 
         precision = precision or os.environ.get("LPI_VISION_PRECISION", DEFAULT_VISION_PRECISION)
-        if precision not in ("bf16", "fp16"):
-            raise ValueError(f"vision precision must be 'bf16' or 'fp16', got {precision!r}")
+        if precision not in ("bf16", "fp16", "fp32"):
+            raise ValueError(f"vision precision must be 'bf16', 'fp16' or 'fp32' (parity mode), got {precision!r}")
         self.precision = precision
-        self.half = torch.float16 if precision == "fp16" else torch.bfloat16
+        self.half = {"fp16": torch.float16, "fp32": torch.float32}.get(precision, torch.bfloat16)
         w = sd[prefix + "conv1.weight"]
         self.width, _, self.patch, _ = w.shape
         self.conv_w = _half(w.reshape(self.width, -1), dev, self.half)
@@ -241,29 +255,66 @@ class VisionEngine:
         self.n_patch = self.pos.shape[0] - 1
         self.dev = dev
 
+    def patch_embed(self, images: torch.Tensor) -> torch.Tensor:
+        """conv1 (kernel = stride = patch, no bias, model.py:228-231) as im2col + one tensor-core GEMM -> [B * n_patch, D] fp32."""
+        patches = ops.im2col_patches(images.contiguous(), self.patch, self.half)
+        if self.precision == "fp32":
+            return ops.gemm_f32(patches, self.conv_w, ops.EPI_F32)
+        return ops.gemm(patches, self.conv_w, ops.EPI_F32)
+
     def forward(self, images: torch.Tensor, prompt_table: Optional[torch.Tensor] = None, sel: Optional[torch.Tensor] = None,
-                tape: Optional[dict] = None, inject_layers: Sequence[int] = ()):
+                tape: Optional[dict] = None, inject_layers: Sequence[int] = (), factors=None, patch_emb: Optional[torch.Tensor] = None,
+                centers: Optional[torch.Tensor] = None):
         """images [B,3,R,R] fp32; prompt_table [T, Lp, P, D] fp32 (layer 0 enters the token sequence, model.py:240-248) or None;
-        sel int32[B] picks the table per sample (None = table 0).  Returns (L2-normalised features, raw projection z), both [B, E] fp32."""
+        sel int32[B] picks the table per sample (None = table 0).  Returns (L2-normalised features, raw projection z), both [B, E] fp32.
+
+        factors = (dim_1_share [T, Lp, r], dim_2_visual [T, P, r], dim_3_visual [T, D, r], scale): the prompt rows are reconstructed inside
+        the assembly kernel (DecomposedPrompt.forward fused with the token concat, prompts.py:38-57 + model.py:240-248) -- no table is
+        materialised for the token sequence; prompt_table is then only needed for opt-in deep injection (inject_layers).
+        patch_emb: the output of patch_embed(images) when the caller runs several passes over the same images (sprompt.py:336-351 +
+        slinet.py:212-220 run the ViT twice per evaluation image).  centers [T, C, E]: the head also returns each sample's task id
+        (third return value, int32 [B]; sprompt.py:336-351)."""
         B = images.shape[0]
         D = self.width
-        patches = ops.im2col_patches(images.contiguous(), self.patch, self.half)
-        pe = ops.gemm(patches, self.conv_w, ops.EPI_F32)
-        P = 0 if prompt_table is None else prompt_table.shape[2]
-        layer0 = None if prompt_table is None else prompt_table[:, 0].contiguous()
-        x = ops.assemble_vision(pe, self.cls, self.pos, layer0, sel, self.ln_pre[0], self.ln_pre[1], B, self.n_patch, P, D)
+        pe = patch_emb if patch_emb is not None else self.patch_embed(images)
+        layer0 = None
+        if factors is not None:
+            P = factors[1].shape[1]
+            x = ops.assemble_vision_factors(pe, self.cls, self.pos, factors, sel, self.ln_pre[0], self.ln_pre[1], B, self.n_patch, D)
+        else:
+            P = 0 if prompt_table is None else prompt_table.shape[2]
+            layer0 = None if prompt_table is None else prompt_table[:, 0].contiguous()
+            x = ops.assemble_vision(pe, self.cls, self.pos, layer0, sel, self.ln_pre[0], self.ln_pre[1], B, self.n_patch, P, D)
         L = 1 + P + self.n_patch
         inject = None
-        if prompt_table is not None and len(inject_layers) > 0:
+        if len(inject_layers) > 0 and P > 0:
+            if prompt_table is None:
+                raise ValueError("deep-prompt injection (inject_layers) needs the reconstructed prompt_table as well as the factors")
             inject = {"layers": set(int(l) for l in inject_layers), "table": prompt_table, "sel": sel, "P": P}
         ttape = TowerTape(B, L) if tape is not None else None
         x = self.tower.forward(x, B, L, ttape, inject)
         rows = torch.arange(B, device=x.device, dtype=torch.int32) * L
-        feat, z = ops.head_fwd(x, rows, self.ln_post[0], self.ln_post[1], self.proj)
+        task_id = None
+        if centers is not None:
+            feat, z, task_id = ops.head_fwd_select(x, rows, self.ln_post[0], self.ln_post[1], self.proj, centers)
+        else:
+            feat, z = ops.head_fwd(x, rows, self.ln_post[0], self.ln_post[1], self.proj)
         if tape is not None:
-            tape.update(dict(tower=ttape, rows=rows, z=z, x=x, layer0=layer0, sel=sel, P=P, L=L, B=B, inject=inject,
-                             n_tables=0 if prompt_table is None else prompt_table.shape[0], Lp=0 if prompt_table is None else prompt_table.shape[1]))
-        return feat, z
+            n_tables = 0 if P == 0 else (factors[0].shape[0] if factors is not None else prompt_table.shape[0])
+            n_layers = 0 if P == 0 else (factors[0].shape[1] if factors is not None else prompt_table.shape[1])
+            tape.update(dict(tower=ttape, rows=rows, z=z, x=x, layer0=layer0, factors=factors, sel=sel, P=P, L=L, B=B, inject=inject,
+                             n_tables=n_tables, Lp=n_layers))
+        return (feat, z, task_id) if centers is not None else (feat, z)
+
+    def select_and_encode(self, images: torch.Tensor, centers: torch.Tensor, prompt_table: Optional[torch.Tensor] = None, factors=None,
+                          inject_layers: Sequence[int] = ()):
+        """The evaluation path of one image batch (sprompt.py:456-470: get_visual_task_id -> visual_interface) with the patch embedding
+        computed ONCE for both ViT passes and the task-id selection produced by the head kernel of the un-prompted pass.
+        -> (prompted features [B, E], sel int32 [B], un-prompted features [B, E])"""
+        pe = self.patch_embed(images)
+        f0, _, sel = self.forward(images, None, None, None, (), None, pe, centers)
+        f, _ = self.forward(images, prompt_table, sel, None, inject_layers, factors, pe)
+        return f, sel, f0
 
     def backward(self, tape: dict, dfeat: Optional[torch.Tensor], dz: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
         """d loss / d prompt_table [T, Lp, P, D] (zero for layers that never entered the encoder).  dfeat = gradient wrt the
@@ -279,7 +330,10 @@ class VisionEngine:
         if P == 0:
             return None
         G = torch.zeros(tape["n_tables"], tape["Lp"], P, D, device=dev, dtype=torch.float32)
-        G[:, 0] = ops.assemble_vision_bwd(g, tape["layer0"], tape["sel"], self.ln_pre[0], B, L, P, tape["n_tables"], D)
+        if tape.get("factors") is not None:
+            G[:, 0] = ops.assemble_vision_factors_bwd(g, tape["factors"], tape["sel"], self.ln_pre[0], B, L, tape["n_tables"], D)
+        else:
+            G[:, 0] = ops.assemble_vision_bwd(g, tape["layer0"], tape["sel"], self.ln_pre[0], B, L, P, tape["n_tables"], D)
         for l, gl in inj_grads.items():
             G[:, l] = gl
         return G
@@ -307,8 +361,10 @@ class TextEngine:
         self.dev = dev
 
     def forward(self, tokens: torch.Tensor, prompt_table: Optional[torch.Tensor] = None, sel: Optional[torch.Tensor] = None,
-                tape: Optional[dict] = None, inject_layers: Sequence[int] = (), text_len: Optional[int] = None):
+                tape: Optional[dict] = None, inject_layers: Sequence[int] = (), text_len: Optional[int] = None, factors=None):
         """tokens int64 [B, 77] on the device; prompt_table [T, Lp, P, Dt] fp32 (layer 0 is spliced over positions 1..P) or None.
+        factors = (dim_1_share [T, Lp, r], dim_2_textual [T, P, r], dim_3_textual [T, Dt, r], scale): the context rows are reconstructed
+        inside the splice kernel instead of being read from a table (see VisionEngine.forward).
 
         text_len (host int, or the `lpi_text_len` attribute the tokenizer attaches to its output): number of leading token positions
         that contain every caption's EOT.  The mask is causal (model.py:347-353) and the head reads the EOT row only, so positions
@@ -318,24 +374,30 @@ class TextEngine:
         D = self.width
         if text_len is None:
             text_len = getattr(tokens, "lpi_text_len", None)
-        n_prompt = 0 if prompt_table is None else prompt_table.shape[2]
+        n_prompt = factors[1].shape[1] if factors is not None else (0 if prompt_table is None else prompt_table.shape[2])
         if text_len is not None and self.trim_padding:
             Lt = max(1 + n_prompt, min(int(text_len), L))
             if Lt < L:
                 tokens, L = tokens[:, :Lt], Lt
-        P = 0 if prompt_table is None else prompt_table.shape[2]
-        layer0 = None if prompt_table is None else prompt_table[:, 0].contiguous()
-        x = ops.assemble_text(self.emb, tokens.contiguous(), self.pos, layer0, sel, B, L, P, D)
+        P = n_prompt
+        if factors is not None:
+            x = ops.assemble_text_factors(self.emb, tokens.contiguous(), self.pos, factors, sel, B, L, D)
+        else:
+            layer0 = None if prompt_table is None else prompt_table[:, 0].contiguous()
+            x = ops.assemble_text(self.emb, tokens.contiguous(), self.pos, layer0, sel, B, L, P, D)
         inject = None
-        if prompt_table is not None and len(inject_layers) > 0:
+        if len(inject_layers) > 0 and P > 0:
+            if prompt_table is None:
+                raise ValueError("deep-prompt injection (inject_layers) needs the reconstructed prompt_table as well as the factors")
             inject = {"layers": set(int(l) for l in inject_layers), "table": prompt_table, "sel": sel, "P": P}
         ttape = TowerTape(B, L) if tape is not None else None
         x = self.tower.forward(x, B, L, ttape, inject)
         rows = (torch.arange(B, device=x.device, dtype=torch.int64) * L + tokens.argmax(dim=-1)).to(torch.int32)   # EOT row
         feat, z = ops.head_fwd(x, rows, self.ln_final[0], self.ln_final[1], self.proj)
         if tape is not None:
-            tape.update(dict(tower=ttape, rows=rows, z=z, x=x, sel=sel, P=P, L=L, B=B, inject=inject,
-                             n_tables=0 if prompt_table is None else prompt_table.shape[0], Lp=0 if prompt_table is None else prompt_table.shape[1]))
+            n_tables = 0 if P == 0 else (factors[0].shape[0] if factors is not None else prompt_table.shape[0])
+            n_layers = 0 if P == 0 else (factors[0].shape[1] if factors is not None else prompt_table.shape[1])
+            tape.update(dict(tower=ttape, rows=rows, z=z, x=x, sel=sel, P=P, L=L, B=B, inject=inject, n_tables=n_tables, Lp=n_layers))
         return feat, z
 
     def backward(self, tape: dict, dfeat: Optional[torch.Tensor], dz: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:

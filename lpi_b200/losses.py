@@ -19,13 +19,19 @@ TASK_THRESHOLD = 0.4          # slinet.py:173
 AUX_WEIGHT = 0.1              # slinet.py:158,161
 
 
+FUSED_INFONCE = __import__("os").environ.get("LPI_FUSED_INFONCE", "1") != "0"     # 0 = the four-launch form (3 fp32 GEMMs + ClipLoss kernels)
+
+
 def contrastive_fwd_bwd(img_f: torch.Tensor, txt_f: torch.Tensor, scale: float, row0: int = 0, n_local: Optional[int] = None,
-                        want_grad: bool = True):
+                        want_grad: bool = True, want_logits: bool = True):
     """base_loss = ClipLoss(scale * I @ T^T) over the GLOBAL batch (img_f, txt_f: all-gathered [n, E] fp32) and its gradient
     for the local rows [row0, row0 + n_local): dI = scale * G[rows, :] @ T, dT = scale * G[:, rows]^T @ I with
     G = (softmax_rows + softmax_cols - 2 I) / (2n)  (loss.py:75-87; slinet.py:138-141)."""
     n = img_f.shape[0]
     n_local = n if n_local is None else n_local
+    if FUSED_INFONCE:
+        # one cooperative launch: similarities, both LSEs, loss and the local gradient rows; the logits are an optional by-product
+        return ops.sim_infonce_fwd_bwd(img_f.contiguous(), txt_f.contiguous(), scale, row0, n_local, 1.0, want_grad, want_logits)
     logits = ops.sgemm(img_f, txt_f.t(), alpha=scale)
     loss, dS = ops.clip_loss_logits(logits, 1.0, want_grad)
     if not want_grad:

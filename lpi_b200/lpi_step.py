@@ -47,15 +47,26 @@ def flat_size(factors: Dict[str, torch.Tensor]) -> int:
 
 def train_step(vision: VisionEngine, text: TextEngine, factors: Dict[str, torch.Tensor], images: torch.Tensor, tokens: torch.Tensor,
                logit_scale: float, prev_prompts: Sequence = (), task_target: Optional[torch.Tensor] = None,
-               inject_layers: Sequence[int] = (), group=None, text_len: Optional[int] = None, overlap_towers: Optional[bool] = None) -> Dict:
+               inject_layers: Sequence[int] = (), group=None, text_len: Optional[int] = None, overlap_towers: Optional[bool] = None,
+               prompt_scale: float = 1.0, want_logits: bool = True) -> Dict:
     """factors: the five fp32 device tensors of the current task's DecomposedPrompt.  images [b,3,224,224] fp32 and
     tokens [b,77] int64 are this rank's slice of the global batch.  prev_prompts: [(vis, txt)] of the frozen earlier
     tasks (task loss, only when non-empty).  Returns losses (0-dim-like device tensors), grads (same keys as factors)
     and the features.  With `group`, features are all-gathered and the gradient all-reduced (sum).  text_len: host-side bound on the
-    EOT positions of `tokens` (see TextEngine.forward; output-exact trimming of the padding after the last EOT)."""
+    EOT positions of `tokens` (see TextEngine.forward; output-exact trimming of the padding after the last EOT).
+    prompt_scale: DecomposedPrompt.scale (prompts.py:26; 1 in the reference).
+
+    The token sequences take their prompt rows straight from the factors (reconstruction fused into the assembly kernels); the
+    [9, 16, D] tables are still reconstructed once per step because the alignment and task losses read all nine layers."""
     if overlap_towers is None:
         overlap_towers = OVERLAP_TOWERS
     vis, txt = reconstruct(factors)
+    if prompt_scale != 1.0:
+        vis, txt = vis * prompt_scale, txt * prompt_scale
+    fv = (factors["dim_1_share"].unsqueeze(0), factors["dim_2_visual"].unsqueeze(0), factors["dim_3_visual"].unsqueeze(0), prompt_scale)
+    ft = (factors["dim_1_share"].unsqueeze(0), factors["dim_2_textual"].unsqueeze(0), factors["dim_3_textual"].unsqueeze(0), prompt_scale)
+    deep = len(inject_layers) > 0                   # opt-in deep injection reads layers >= 1 of the table
+    vtab, ttab = (vis.unsqueeze(0), txt.unsqueeze(0)) if deep else (None, None)
     vtape, ttape = {}, {}
     side = _side_stream(images.device) if overlap_towers else None
     main = torch.cuda.current_stream()
@@ -64,13 +75,13 @@ def train_step(vision: VisionEngine, text: TextEngine, factors: Dict[str, torch.
         # wave), so it runs on a second stream next to the vision tower and fills the SMs that tower's non-persistent kernels leave idle
         side.wait_stream(main)
         with torch.cuda.stream(side):
-            txt_f, _ = text.forward(tokens, txt.unsqueeze(0), None, ttape, inject_layers, text_len=text_len)
-        img_f, _ = vision.forward(images, vis.unsqueeze(0), None, vtape, inject_layers)
+            txt_f, _ = text.forward(tokens, ttab, None, ttape, inject_layers, text_len=text_len, factors=ft)
+        img_f, _ = vision.forward(images, vtab, None, vtape, inject_layers, factors=fv)
         main.wait_stream(side)
         _record(txt_f, main)
     else:
-        img_f, _ = vision.forward(images, vis.unsqueeze(0), None, vtape, inject_layers)
-        txt_f, _ = text.forward(tokens, txt.unsqueeze(0), None, ttape, inject_layers, text_len=text_len)
+        img_f, _ = vision.forward(images, vtab, None, vtape, inject_layers, factors=fv)
+        txt_f, _ = text.forward(tokens, ttab, None, ttape, inject_layers, text_len=text_len, factors=ft)
     b = img_f.shape[0]
     rank, world = 0, 1
     all_img, all_txt = img_f, txt_f
@@ -84,7 +95,8 @@ def train_step(vision: VisionEngine, text: TextEngine, factors: Dict[str, torch.
             dist.all_gather_into_tensor(gathered, both, group=group)
             E = img_f.shape[1]
             all_img, all_txt = gathered[:, :E].contiguous(), gathered[:, E:].contiguous()
-    base, d_img, d_txt, logits = losses.contrastive_fwd_bwd(all_img, all_txt, logit_scale, rank * b, b)
+    # similarities + InfoNCE + their backward in one launch; the B x B logits are written only when asked for (want_logits)
+    base, d_img, d_txt, logits = losses.contrastive_fwd_bwd(all_img, all_txt, logit_scale, rank * b, b, want_logits=want_logits)
     if side is not None:
         side.wait_stream(main)
         _record(d_txt, side)
@@ -98,7 +110,7 @@ def train_step(vision: VisionEngine, text: TextEngine, factors: Dict[str, torch.
         G_txt = text.backward(ttape, d_txt)[0]
     if world > 1:
         # replicated terms (alignment / task losses) are added once after the all-reduce, not world times
-        enc = _factor_grads(factors, G_vis, G_txt)
+        enc = _factor_grads(factors, G_vis * prompt_scale if prompt_scale != 1.0 else G_vis, G_txt * prompt_scale if prompt_scale != 1.0 else G_txt)
         fg = torch.cat([enc[k].reshape(-1) for k in FACTOR_NAMES])      # 5 284 floats = 21 KB: one flat buffer, one collective
         dist.all_reduce(fg, op=dist.ReduceOp.SUM, group=group)
         G_vis = torch.zeros_like(G_vis)
@@ -109,6 +121,8 @@ def train_step(vision: VisionEngine, text: TextEngine, factors: Dict[str, torch.
         vs = torch.stack([p[0].reshape(-1) for p in prev_prompts] + [vis.reshape(-1)])
         ts = torch.stack([p[1].reshape(-1) for p in prev_prompts] + [txt.reshape(-1)])
         out_losses["task_loss"] = losses.task_fwd_bwd(vs, ts, task_target, G_vis, G_txt)
+    if prompt_scale != 1.0:                        # G_* are gradients w.r.t. the SCALED tables
+        G_vis, G_txt = G_vis * prompt_scale, G_txt * prompt_scale
     grads = _factor_grads(factors, G_vis, G_txt)
     if world > 1:
         off = 0

@@ -81,6 +81,73 @@ def gemm_tf32(a: torch.Tensor, w: torch.Tensor, epi: int, bias: Optional[torch.T
     return out
 
 
+def gemm_f32(a: torch.Tensor, w: torch.Tensor, epi: int, bias: Optional[torch.Tensor] = None, resid: Optional[torch.Tensor] = None,
+             out: Optional[torch.Tensor] = None, out2: Optional[torch.Tensor] = None, aux: Optional[torch.Tensor] = None,
+             tile_n: int = 0) -> torch.Tensor:
+    """fp32 parity mode (north_star "1e-5 in fp32"): out[M,N] = epilogue(a[M,K] @ w[N,K]^T) with EXACT fp32 products on the SIMT pipes
+    (lpi_sgemm_bias_f32 + fp32 QuickGELU kernels); same signature as gemm_tf32, fp32 tensors throughout.  A test mode, not a fast one."""
+    _lib.require_device()
+    _chk(a, torch.float32, "a")
+    _chk(w, torch.float32, "w")
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K
+    if out is None:
+        out = torch.empty(M, N, device=a.device, dtype=torch.float32)
+    _chk(out, torch.float32, "out")
+
+    def mm(dst, beta, b):
+        call("sgemm_bias_f32", ptr(a), ptr(w), ptr(b), ptr(dst), M, N, K, C.c_longlong(K), C.c_longlong(1), C.c_longlong(1), C.c_longlong(K),
+             C.c_longlong(dst.stride(0)), C.c_float(1.0), C.c_float(beta), stream_ptr())
+        _count()
+
+    if epi in (EPI_F32, EPI_BF16):
+        mm(out, 0.0, None)
+    elif epi in (EPI_BIAS_F32, EPI_BIAS_BF16):
+        mm(out, 0.0, bias)
+    elif epi == EPI_BIAS_RESID_F32:
+        if out.data_ptr() != resid.data_ptr():
+            out.copy_(resid)
+        mm(out, 1.0, bias)
+    elif epi == EPI_ACC_F32:
+        mm(out, 1.0, None)
+    elif epi == EPI_BIAS_GELU_F32:
+        z = out2 if out2 is not None else torch.empty_like(out)
+        mm(z, 0.0, bias)
+        call("quick_gelu_f32", ptr(z), ptr(out), C.c_longlong(z.numel()), stream_ptr())
+        _count()
+    elif epi == EPI_DGELU_F32:
+        mm(out, 0.0, None)
+        _chk(aux, torch.float32, "aux")
+        call("quick_gelu_bwd_f32", ptr(out), ptr(aux), ptr(out), C.c_longlong(out.numel()), stream_ptr())
+        _count()
+    else:
+        raise _lib.LpiError(f"gemm_f32: epilogue {epi} is not part of the fp32 parity mode")
+    return out
+
+
+def attn_fwd_f32(qkv: torch.Tensor, B: int, L: int, H: int, causal: bool):
+    """fp32 parity mode: qkv [B*L, 3*H*64] fp32 -> (out [B*L, H*64] fp32, lse [B*H*L] natural log)."""
+    _lib.require_device()
+    _chk(qkv, torch.float32, "qkv")
+    assert qkv.shape == (B * L, 3 * H * 64)
+    out = torch.empty(B * L, H * 64, device=qkv.device, dtype=torch.float32)
+    lse = torch.empty(B * H * L, device=qkv.device, dtype=torch.float32)
+    call("attn_fwd_f32", ptr(qkv), ptr(out), ptr(lse), B, L, H, int(causal), stream_ptr())
+    _count()
+    return out, lse
+
+
+def attn_bwd_f32(qkv, out, d_out, lse, B: int, L: int, H: int, causal: bool):
+    for t, n in ((qkv, "qkv"), (out, "out"), (d_out, "d_out"), (lse, "lse")):
+        _chk(t, torch.float32, n)
+    delta = torch.empty(B * H * L, device=qkv.device, dtype=torch.float32)
+    dqkv = torch.empty_like(qkv)
+    call("attn_bwd_f32", ptr(qkv), ptr(out), ptr(d_out), ptr(lse), ptr(delta), ptr(dqkv), B, L, H, int(causal), stream_ptr())
+    _count(2)
+    return dqkv
+
+
 # ------------------------------------------------------------------------------------------ scorer
 def sim_topk_chunks(n_queries: int, n_gallery: int) -> int:
     n = C.c_int()
@@ -343,13 +410,15 @@ def layernorm_bwd(dy, x, gamma, g, g_bf16=None, accumulate=True, grad_scale: Opt
 
 
 def im2col_patches(images: torch.Tensor, patch: int, half_dtype=torch.bfloat16) -> torch.Tensor:
+    """half_dtype: bf16 / fp16 GEMM operand rows, or torch.float32 for the fp32 parity mode."""
     _lib.require_device()
     _chk(images, torch.float32, "images")
     B, ch, R, _ = images.shape
     assert ch == 3
     G = R // patch
     out = torch.empty(B * G * G, 3 * patch * patch, device=images.device, dtype=half_dtype)
-    call("im2col_patches_f16" if half_dtype == torch.float16 else "im2col_patches", ptr(images), ptr(out), B, R, patch, stream_ptr())
+    name = {torch.float16: "im2col_patches_f16", torch.float32: "im2col_patches_f32"}.get(half_dtype, "im2col_patches")
+    call(name, ptr(images), ptr(out), B, R, patch, stream_ptr())
     _count()
     return out
 
@@ -358,6 +427,44 @@ def assemble_vision(patch_emb, cls, pos, prompt_table, sel, ln_g, ln_b, B, n_pat
     x = torch.empty(B * (1 + P + n_patch), D, device=patch_emb.device, dtype=torch.float32)
     call("assemble_vision", ptr(patch_emb), ptr(cls), ptr(pos), ptr(prompt_table), ptr(sel), ptr(ln_g), ptr(ln_b), ptr(x), B, n_patch, P, D,
          C.c_float(LN_EPS), stream_ptr())
+    _count()
+    return x
+
+
+def _factor_args(fac):
+    """fac = (dim1_share [T, Lp, r], dim2 [T, P, r], dim3 [T, D, r], scale) -> ctypes args of the *_factors entry points."""
+    d1, d2, d3, scale = fac
+    for t in (d1, d2, d3):
+        _chk(t, torch.float32, "factor")
+    if d1.dim() != 3 or d2.dim() != 3 or d3.dim() != 3 or not (d1.shape[0] == d2.shape[0] == d3.shape[0]) or not (d1.shape[2] == d2.shape[2] == d3.shape[2]):
+        raise _lib.LpiError("factors must be dim1 [T, Lp, r], dim2 [T, P, r], dim3 [T, D, r]")
+    return ptr(d1), ptr(d2), ptr(d3), d1.shape[2], d1.shape[1], C.c_float(float(scale))
+
+
+def assemble_vision_factors(patch_emb, cls, pos, fac, sel, ln_g, ln_b, B, n_patch, D):
+    """assemble_vision with the prompt rows reconstructed in the kernel from the DecomposedPrompt factors (no table)."""
+    P = fac[1].shape[1]
+    x = torch.empty(B * (1 + P + n_patch), D, device=patch_emb.device, dtype=torch.float32)
+    call("assemble_vision_factors", ptr(patch_emb), ptr(cls), ptr(pos), *_factor_args(fac), ptr(sel), ptr(ln_g), ptr(ln_b), ptr(x), B, n_patch, P, D,
+         C.c_float(LN_EPS), stream_ptr())
+    _count()
+    return x
+
+
+def assemble_vision_factors_bwd(g, fac, sel, ln_g, B, L, n_tables, D):
+    P = fac[1].shape[1]
+    d = torch.empty(n_tables, P, D, device=g.device, dtype=torch.float32)
+    call("assemble_vision_factors_bwd", ptr(g), *_factor_args(fac), ptr(sel), ptr(ln_g), ptr(d), B, L, P, n_tables, D, C.c_float(LN_EPS), stream_ptr())
+    _count()
+    return d
+
+
+def assemble_text_factors(emb, tokens, pos, fac, sel, B, L, D):
+    _lib.require_device()
+    _chk(tokens, torch.int64, "tokens")
+    P = fac[1].shape[1]
+    x = torch.empty(B * L, D, device=emb.device, dtype=torch.float32)
+    call("assemble_text_factors", ptr(emb), ptr(tokens), ptr(pos), *_factor_args(fac), ptr(sel), ptr(x), B, L, P, D, stream_ptr())
     _count()
     return x
 
@@ -401,6 +508,23 @@ def head_fwd(x, row_idx, ln_g, ln_b, proj):
     call("head_fwd", ptr(x), ptr(row_idx), ptr(ln_g), ptr(ln_b), ptr(proj), ptr(z), ptr(f), B, D, E, C.c_float(LN_EPS), stream_ptr())
     _count(2)
     return f, z
+
+
+def head_fwd_select(x, row_idx, ln_g, ln_b, proj, centers):
+    """head_fwd + task-id selection in its last kernel: -> (feat, z, sel int32 [B]); centers [T, C, E] fp32 (sprompt.py:336-368)."""
+    _chk(x, torch.float32, "x")
+    _chk(row_idx, torch.int32, "row_idx")
+    _chk(centers, torch.float32, "centers")
+    B = row_idx.shape[0]
+    D, E = proj.shape
+    T, Cn, _ = centers.shape
+    z = torch.empty(B, E, device=x.device, dtype=torch.float32)
+    f = torch.empty(B, E, device=x.device, dtype=torch.float32)
+    sel = torch.empty(B, device=x.device, dtype=torch.int32)
+    call("head_fwd_select", ptr(x), ptr(row_idx), ptr(ln_g), ptr(ln_b), ptr(proj), ptr(z), ptr(f), ptr(centers), T, Cn, ptr(sel), B, D, E,
+         C.c_float(LN_EPS), stream_ptr())
+    _count(2)
+    return f, z, sel
 
 
 def head_bwd(dfeat, dz, z, x, row_idx, ln_g, proj, g, g_bf16=None, grad_scale: Optional[float] = None):
@@ -476,6 +600,27 @@ def clip_loss_logits(logits: torch.Tensor, weight: float = 1.0, want_grad: bool 
     call("clip_loss_logits", ptr(logits), n, C.c_float(weight), ptr(ws), ptr(loss), ptr(d), stream_ptr())
     _count(3 if want_grad else 2)
     return loss, d
+
+
+def sim_infonce_fwd_bwd(img_f: torch.Tensor, txt_f: torch.Tensor, scale: float, row0: int = 0, n_local: Optional[int] = None,
+                        weight: float = 1.0, want_grad: bool = True, want_logits: bool = False):
+    """ONE launch: loss = weight * ClipLoss(scale * I @ T^T) over the global batch + gradients of the local feature rows
+    -> (loss [1], d_img [n_local, E] or None, d_txt [n_local, E] or None, logits [n, n] or None)."""
+    _lib.require_device()
+    _chk(img_f, torch.float32, "img_f")
+    _chk(txt_f, torch.float32, "txt_f")
+    n, E = img_f.shape
+    assert txt_f.shape == (n, E)
+    n_local = n if n_local is None else n_local
+    ws = torch.empty(4 * n, device=img_f.device, dtype=torch.float32)
+    loss = torch.empty(1, device=img_f.device, dtype=torch.float32)
+    logits = torch.empty(n, n, device=img_f.device, dtype=torch.float32) if want_logits else None
+    d_img = torch.empty(n_local, E, device=img_f.device, dtype=torch.float32) if want_grad else None
+    d_txt = torch.empty(n_local, E, device=img_f.device, dtype=torch.float32) if want_grad else None
+    call("sim_infonce_fwd_bwd", ptr(img_f), ptr(txt_f), n, E, C.c_float(scale), C.c_float(weight), row0, n_local, ptr(ws),
+         C.c_void_p(ws.data_ptr() + 8 * n), ptr(loss), ptr(logits), ptr(d_img), ptr(d_txt), stream_ptr())
+    _count()
+    return loss, d_img, d_txt, logits
 
 
 def row_mean(x: torch.Tensor, scale: float = 1.0):

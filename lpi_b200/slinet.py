@@ -132,12 +132,48 @@ class SliNet(nn.Module):
             ps = [p() for p in self.prompts]
         return torch.stack([p[0] for p in ps]), torch.stack([p[1] for p in ps])        # [T,9,16,768], [T,9,16,512]
 
+    def _factor_stacks(self):
+        """The factors of ALL tasks stacked ([T, Lp, r], [T, P, r], [T, D, r] per modality) for the kernels that reconstruct prompt rows
+        on the fly.  Rebuilt on every call (five tiny concatenations): the fused SGD kernel updates the factors in place through raw
+        pointers, so parameter version counters cannot be trusted for caching."""
+        with torch.no_grad():
+            st = lambda name: torch.stack([getattr(pr, name).detach().float() for pr in self.prompts]).contiguous()
+            out = {"d1": st("dim_1_share"), "d2v": st("dim_2_visual"), "d2t": st("dim_2_textual"), "d3v": st("dim_3_visual"),
+                   "d3t": st("dim_3_textual")}
+        scales = {float(pr.scale) for pr in self.prompts}
+        out["scale"] = scales.pop() if len(scales) == 1 else None      # per-task scales differ: fall back to the tables
+        return out
+
+    def _fused_eval(self) -> bool:
+        """Evaluation interfaces take the fused path (prompt rows reconstructed inside the assembly kernels, no [T,9,16,D] tables) unless
+        autograd has to see the prompts or deep injection needs layers >= 1 of the tables."""
+        return (not torch.is_grad_enabled()) and len(self.clip_model.inject_layers) == 0 and len({float(pr.scale) for pr in self.prompts}) == 1
+
     def visual_interface(self, image, image_category):
         """slinet.py:212-220: every sample uses the prompts of its (predicted) task."""
-        vt, _ = self._prompt_tables()
         sel = torch.as_tensor(image_category, device=image.device).to(torch.int32).contiguous()
+        if self._fused_eval():
+            f = self._factor_stacks()
+            return self.image_encoder.engine().forward(image.float(), None, sel, factors=(f["d1"], f["d2v"], f["d3v"], f["scale"]))[0]
+        vt, _ = self._prompt_tables()
         from .autograd import VisionEncodeFn
         return VisionEncodeFn.apply(self.image_encoder.engine(), image.float(), vt, sel, tuple(self.image_encoder.inject_layers))[0]
+
+    @torch.no_grad()
+    def visual_select_and_encode(self, image, task_keys):
+        """get_visual_task_id + visual_interface of one image batch (sprompt.py:336-351, 456-470; slinet.py:212-220) as the evaluation
+        loop needs them: the patch embedding is computed once for the un-prompted and the prompted ViT pass, the task-id selection comes
+        out of the un-prompted pass's head kernel.  task_keys: list of [5, E] K-Means centres per task.
+        -> (features [B, E], selection int64 [B])"""
+        centers = torch.stack([k.float() for k in task_keys]).contiguous()
+        eng = self.image_encoder.engine()
+        if self._fused_eval():
+            f = self._factor_stacks()
+            feat, sel, _ = eng.select_and_encode(image.float(), centers, None, (f["d1"], f["d2v"], f["d3v"], f["scale"]))
+        else:
+            vt, _ = self._prompt_tables()
+            feat, sel, _ = eng.select_and_encode(image.float(), centers, vt, None, tuple(self.image_encoder.inject_layers))
+        return feat, sel.long()
 
     def textual_interface(self, text, text_category):
         """slinet.py:185-210.  Eval: one batched pass (the reference loops per sample in Python).  Train: classifier_pool ctx."""
@@ -145,9 +181,12 @@ class SliNet(nn.Module):
         if self.training:
             a, b = pl(text, None)
             return self.text_encoder.encode(a, b, None)[0]
-        _, tt = self._prompt_tables()
         tokenized = text if isinstance(text, torch.Tensor) else pl.tokenize(text)
         sel = torch.as_tensor(text_category, device=tokenized.device).to(torch.int32).contiguous()
+        if self._fused_eval():
+            f = self._factor_stacks()
+            return self.clip_model.text_engine().forward(tokenized, None, sel, factors=(f["d1"], f["d2t"], f["d3t"], f["scale"]))[0]
+        _, tt = self._prompt_tables()
         return TextEncodeFn.apply(self.clip_model.text_engine(), tokenized, tt, sel, tuple(self.clip_model.inject_layers))[0]
 
     def update_fc(self, nb_classes):

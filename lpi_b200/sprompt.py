@@ -325,7 +325,8 @@ class SPrompts(object):
         text_len = getattr(tokens, "lpi_text_len", None)
 
         def run(images, tokens, text_len):
-            r = lpi_step.train_step(vision, text, factors, images, tokens, scale, prev, target, inject, self.group, text_len=text_len)
+            r = lpi_step.train_step(vision, text, factors, images, tokens, scale, prev, target, inject, self.group, text_len=text_len,
+                                    prompt_scale=float(prompt.scale))
             for k in lpi_step.FACTOR_NAMES:
                 getattr(prompt, k).grad = r["grads"][k]
             optimizer.step()
@@ -438,8 +439,9 @@ class SPrompts(object):
             if self.args["prompt_type"] == "clip":
                 feat = self._network.extract_vector(image)
             else:
-                selection = self.get_visual_task_id(image)
-                feat = self._network.visual_interface(image, selection)
+                # get_visual_task_id + visual_interface with the patch embedding shared by both ViT passes and the selection produced by
+                # the un-prompted pass's head kernel
+                feat, _ = self._network.visual_select_and_encode(image, self.all_keys)
             image_feats.append(feat)
             category_i.extend(int(z) for z in category)
         image_feats = torch.cat(image_feats)

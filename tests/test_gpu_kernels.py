@@ -243,6 +243,35 @@ def test_clip_loss_and_contrastive(n):
         r0, nl = n // 4, n // 2
         _, dI2, dT2, _ = losses.contrastive_fwd_bwd(I, T, s, r0, nl)
         assert torch.equal(dI2, dI[r0:r0 + nl]) and torch.equal(dT2, dT[r0:r0 + nl])
+    # the one-launch fused kernel against the four-launch form (3 fp32 GEMMs + ClipLoss kernels) and its optional logits
+    assert losses.FUSED_INFONCE and (lg.cpu() - (s * Ir @ Tr.t()).detach()).abs().max() < 2e-5
+    losses.FUSED_INFONCE = False
+    try:
+        loss_u, dI_u, dT_u, lg_u = losses.contrastive_fwd_bwd(I, T, s)
+    finally:
+        losses.FUSED_INFONCE = True
+    assert abs(float(loss) - float(loss_u)) < 2e-6 * max(1.0, abs(float(loss_u))) and (lg - lg_u).abs().max() < 2e-5
+    assert _rel(dI, dI_u) < 1e-5 and _rel(dT, dT_u) < 1e-5
+    l0, a0, b0, none = ops.sim_infonce_fwd_bwd(I, T, s, want_grad=False, want_logits=False)
+    assert a0 is None and b0 is None and none is None and float(l0) == float(loss)
+    w_loss, w_dI, _, _ = ops.sim_infonce_fwd_bwd(I, T, s, weight=0.1)
+    assert abs(float(w_loss) - 0.1 * float(loss)) < 1e-6 and _rel(w_dI, 0.1 * dI) < 1e-6
+
+
+def test_fused_infonce_large_global_batch():
+    """n = 1000 (a global batch of 8 x 125, not a multiple of anything convenient), E = 512: loss and both gradients vs fp64 autograd."""
+    g = torch.Generator().manual_seed(77)
+    n, E, s = 1000, 512, 1 / 0.07
+    I = F.normalize(torch.randn(n, E, generator=g), dim=-1)
+    T = F.normalize(0.3 * I + torch.randn(n, E, generator=g) / E ** 0.5, dim=-1)
+    Ir, Tr = I.double().requires_grad_(True), T.double().requires_grad_(True)
+    S_ = s * Ir @ Tr.t()
+    lab = torch.arange(n)
+    ref = 0.5 * (F.cross_entropy(S_, lab) + F.cross_entropy(S_.t(), lab))
+    ref.backward()
+    loss, dI, dT, lg = ops.sim_infonce_fwd_bwd(I.cuda(), T.cuda(), s, 125 * 3, 125, want_logits=False)
+    assert lg is None and abs(float(loss) - float(ref)) < 1e-5 * float(ref)
+    assert _rel(dI.cpu(), Ir.grad[375:500]) < 2e-5 and _rel(dT.cpu(), Tr.grad[375:500]) < 2e-5
 
 
 def test_alignment_and_task_loss():
@@ -296,3 +325,55 @@ def test_sgemm_strided():
     assert (ops.sgemm(at.t(), b) - at.t() @ b).abs().max() < 1e-4
     bt = torch.randn(130, 33, generator=g).cuda()
     assert (ops.sgemm(a, bt.t()) - a @ bt.t()).abs().max() < 1e-4
+
+
+def test_factor_fused_assembly_is_bit_identical_to_reconstruct_then_assemble():
+    """north_star subsystem 1: DecomposedPrompt.forward (prompts.py:38-57) fused with the token concat (model.py:240-248,
+    prompt_learner.py:152-163): the assembly kernels rebuild the prompt rows from the stacked factors of T tasks (per-sample task
+    selection) and must equal lpi_prompt_fwd -> table -> assemble bit for bit, forward and backward, with and without a scale."""
+    from lpi_b200 import synthetic as S
+
+    g = torch.Generator().manual_seed(41)
+    B, n_patch, P, Dv, Dt, T, Lp, r = 6, 196, 16, 768, 512, 3, 9, 4
+    facs = [{k: v.cuda() for k, v in S.make_prompt_factors(40 + t).items()} for t in range(T)]
+    st = lambda name: torch.stack([f[name] for f in facs]).contiguous()
+    tabs = [ops.prompt_fwd(*[f[k] for k in O.FACTOR_NAMES]) for f in facs]
+    vt = torch.stack([t[0][0] for t in tabs]).contiguous()            # layer 0 of every task: [T, P, Dv]
+    tt = torch.stack([t[1][0] for t in tabs]).contiguous()
+    sel = torch.tensor([2, 0, 1, 1, 2, 0], dtype=torch.int32).cuda()
+    pe = torch.randn(B * n_patch, Dv, generator=g).cuda()
+    cls, pos = torch.randn(Dv, generator=g).cuda(), torch.randn(n_patch + 1, Dv, generator=g).cuda()
+    gam, bet = (1 + 0.1 * torch.randn(Dv, generator=g)).cuda(), (0.1 * torch.randn(Dv, generator=g)).cuda()
+    for scale in (1.0, 0.5):
+        fv = (st("dim_1_share"), st("dim_2_visual"), st("dim_3_visual"), scale)
+        ft = (st("dim_1_share"), st("dim_2_textual"), st("dim_3_textual"), scale)
+        for s_ in (sel, None):
+            x = ops.assemble_vision_factors(pe, cls, pos, fv, s_, gam, bet, B, n_patch, Dv)
+            want = ops.assemble_vision(pe, cls, pos, (vt * scale).contiguous(), s_, gam, bet, B, n_patch, P, Dv)
+            assert torch.equal(x, want), (scale, s_ is None)
+        L = 1 + P + n_patch
+        gup = torch.randn(B * L, Dv, generator=g).cuda()
+        d = ops.assemble_vision_factors_bwd(gup, fv, sel, gam, B, L, T, Dv)
+        assert torch.equal(d, ops.assemble_vision_bwd(gup, (vt * scale).contiguous(), sel, gam, B, L, P, T, Dv))
+        V, Lt = 1000, 40
+        emb, tpos = torch.randn(V, Dt, generator=g).cuda(), torch.randn(77, Dt, generator=g).cuda()
+        tok = torch.randint(0, V, (B, Lt), generator=g).cuda()
+        xt = ops.assemble_text_factors(emb, tok, tpos, ft, sel, B, Lt, Dt)
+        assert torch.equal(xt, ops.assemble_text(emb, tok, tpos, (tt * scale).contiguous(), sel, B, Lt, P, Dt))
+
+
+def test_head_fwd_select_equals_head_plus_nearest_center():
+    g = torch.Generator().manual_seed(43)
+    B, L, D, E, T = 37, 5, 768, 512, 6
+    x = torch.randn(B * L, D, generator=g).cuda()
+    rows = (torch.arange(B) * L).to(torch.int32).cuda()
+    gam, bet = (1 + 0.1 * torch.randn(D, generator=g)).cuda(), (0.1 * torch.randn(D, generator=g)).cuda()
+    proj = (torch.randn(D, E, generator=g) * D ** -0.5).cuda()
+    f, z = ops.head_fwd(x, rows, gam, bet, proj)
+    keys = F.normalize(torch.randn(T, 5, E, generator=g), dim=-1).cuda()
+    keys[4, 2] = f[11]                                                 # an exact hit
+    keys[1, 0] = keys[3, 4]                                            # a tie between tasks: the first one wins
+    f2, z2, sel = ops.head_fwd_select(x, rows, gam, bet, proj, keys.contiguous())
+    assert torch.equal(f, f2) and torch.equal(z, z2)
+    want = ops.nearest_center_l1(f, keys.contiguous())
+    assert torch.equal(sel.long(), want) and int(sel[11]) == 4

@@ -166,3 +166,69 @@ def test_graphed_train_step_equals_eager(engines):
     ra = lpi_step.train_step(vision, text, fa, images2, tokens, 1 / 0.07, text_len=text_len)
     rb = g.step(images2)
     assert abs(float(ra["losses"]["base_loss"]) - float(rb["losses"]["base_loss"])) < 1e-6
+
+
+def test_shared_patch_embed_and_fused_task_id_equal_the_two_pass_form(engines):
+    """evaluation of an image batch = un-prompted pass -> task id -> prompted pass (sprompt.py:336-351, 456-470).
+    select_and_encode computes the patch embedding once, takes the selection from the un-prompted head kernel and rebuilds the prompt
+    rows from the stacked factors; it must equal the separate calls bit for bit."""
+    vision, _ = engines
+    images = S.make_images(6, 11).cuda()
+    T = 3
+    facs = [{k: v.cuda() for k, v in S.make_prompt_factors(20 + t).items()} for t in range(T)]
+    tabs = torch.stack([lpi_step.reconstruct(f)[0] for f in facs])                     # [T, 9, 16, 768]
+    f0, _ = vision.forward(images, None)
+    keys = torch.nn.functional.normalize(torch.randn(T, 5, 512, generator=torch.Generator().manual_seed(3)), dim=-1).cuda()
+    keys[2, 0] = f0[1]
+    keys[1, 3] = f0[4]
+    sel_want = ops.nearest_center_l1(f0, keys.contiguous()).to(torch.int32)
+    assert int(sel_want[1]) == 2 and int(sel_want[4]) == 1
+    f_want, _ = vision.forward(images, tabs, sel_want)
+    st = lambda name: torch.stack([f[name] for f in facs]).contiguous()
+    fac = (st("dim_1_share"), st("dim_2_visual"), st("dim_3_visual"), 1.0)
+    f, sel, f0b = vision.select_and_encode(images, keys.contiguous(), None, fac)
+    assert torch.equal(sel, sel_want) and torch.equal(f0b, f0) and torch.equal(f, f_want)
+    f2, sel2, _ = vision.select_and_encode(images, keys.contiguous(), tabs, None)      # table form of the same call
+    assert torch.equal(sel2, sel_want) and torch.equal(f2, f_want)
+
+
+def test_prompt_scale_in_the_fused_step(engines):
+    """DecomposedPrompt.scale (prompts.py:26): L(d1; scale = 2) = L(2 d1; scale = 1), so the losses agree, d/d dim_1_share doubles and the
+    other four gradients are unchanged."""
+    vision, text = engines
+    images, tokens = S.make_images(3, 5).cuda(), S.make_tokens(3, 5).cuda()
+    fa = {k: v.cuda() for k, v in S.make_prompt_factors(9).items()}
+    fb = {k: v.clone() for k, v in fa.items()}
+    fb["dim_1_share"] = fb["dim_1_share"] * 2
+    ra = lpi_step.train_step(vision, text, fa, images, tokens, 1 / 0.07, prompt_scale=2.0)
+    rb = lpi_step.train_step(vision, text, fb, images, tokens, 1 / 0.07)
+    for k in ra["losses"]:
+        assert abs(float(ra["losses"][k]) - float(rb["losses"][k])) < 1e-5 * max(1.0, abs(float(rb["losses"][k]))), k
+    for k in O.FACTOR_NAMES:
+        want = rb["grads"][k] * (2.0 if k == "dim_1_share" else 1.0)
+        assert _rel(ra["grads"][k], want) < 1e-4, k
+
+
+@pytest.mark.parametrize("batch", [4, 64])
+def test_fp32_parity_mode_matches_reference_to_1e5(clip_sd, golden_model, golden_b64, batch):
+    """north_star: "embeddings, logits and loss must match within 1e-2 relative in bf16 (1e-5 in fp32)".  precision="fp32" runs both towers
+    on exact-fp32 SIMT kernels (no tensor-core operand rounding): features, logits and losses within 1e-5, the 5 284 prompt gradients
+    within 1e-4 of the real reference's fp32 CPU run, at B = 4 and at the BASELINE batch B = 64, task 1 and task 2."""
+    dev = torch.device("cuda")
+    vision, text = VisionEngine(clip_sd, dev, precision="fp32"), TextEngine(clip_sd, dev, precision="fp32")
+    g = golden_model if batch == 4 else golden_b64
+    images = S.make_images(batch, g["meta"].get("image_seed", 0)).cuda()
+    tokens = g["tokens"].cuda()
+    sim = np.loadtxt(os.path.join(os.path.dirname(os.path.abspath(ops.__file__)), "MID", "task_sim_matrix.txt"))
+    tgt = torch.tensor((sim[:2, :2] > 0.4).astype(np.int32)).cuda()
+    for task in (1, 2):
+        fac = {k: v.cuda() for k, v in S.make_prompt_factors(task - 1).items()}
+        prev = [] if task == 1 else [lpi_step.reconstruct({k: v.cuda() for k, v in S.make_prompt_factors(0).items()})]
+        r = lpi_step.train_step(vision, text, fac, images, tokens, float(np.exp(np.log(1 / 0.07))), prev, tgt if task == 2 else None)
+        want = g[f"step_task{task}"]
+        assert _rel(r["img_f"], want["img_f"]) < 1e-5 and _rel(r["txt_f"], want["txt_f"]) < 1e-5, (task, _rel(r["img_f"], want["img_f"]), _rel(r["txt_f"], want["txt_f"]))
+        assert _rel(r["logits"], want["logits"]) < 1e-5, (task, _rel(r["logits"], want["logits"]))
+        for k, v in want["losses"].items():
+            assert abs(float(r["losses"][k]) - v) < 1e-5 * max(abs(v), 1e-3), (task, k, float(r["losses"][k]), v)
+        for k in O.FACTOR_NAMES:
+            assert _rel(r["grads"][k], want["grads"][k]) < 1e-4, (task, k, _rel(r["grads"][k], want["grads"][k]))

@@ -1,7 +1,7 @@
 """Prints the parity margins of the fused training step against the real-reference golden fixtures (tests/golden/model_b4_seed0.pt and
 model_b64_seed0.pt): feature / logits / loss / prompt-gradient errors per (vision precision, text precision).
 Bars (BASELINE.json north_star): features, logits, losses 1e-2 relative; gradients 2e-2.
-    python tools/parity_margins.py [vision:text ...]       e.g.  bf16:fp16 fp16:fp16"""
+    python tools/parity_margins.py [vision:text ...]       e.g.  bf16:fp16 fp16:fp16 fp32:fp32 (the exact-fp32 parity mode; bars 1e-5 / 1e-4)"""
 import os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
