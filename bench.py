@@ -630,6 +630,11 @@ def train_leg(dev, world, rank, group, steps, warmup, peaks, args, batch_per_gpu
         del r_dp
         torch.cuda.empty_cache()
 
+    # first-step losses on the untouched factors (the reference legs report theirs at the same point: same images, captions and weights)
+    r_first = lpi_step.train_step(vision, text, fac0, images, tokens, 1 / 0.07, group=group, text_len=text_len)
+    loss_first = {k: float(v) for k, v in r_first["losses"].items()}
+    del r_first
+
     def eager_step():
         r = lpi_step.train_step(vision, text, fac, images, tokens, 1 / 0.07, group=group, text_len=text_len)
         opt.step(r["grads"])
@@ -691,7 +696,7 @@ def train_leg(dev, world, rank, group, steps, warmup, peaks, args, batch_per_gpu
     out = {"metric": "prompted_clip_train_pairs_per_sec", "value": gb / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms,
            "global_batch": gb, "parallelism": f"dp{world}", "launch_mode": mode, "launches_per_step": launches_per_step,
            "algorithmic_tflops": gb * g_alg / (ms * 1e-3) / 1e3, "executed_tflops": gb * g_exe / (ms * 1e-3) / 1e3,
-           "loss": float(r["losses"]["base_loss"]),
+           "loss": float(r["losses"]["base_loss"]), "loss_first_step": loss_first, "loss_first_step_sum": sum(loss_first.values()),
            "precision": f"vision {vision.precision} / text fp16 operands, fp32 accumulate, fp32 residual stream / LayerNorm / heads / losses",
            "text_positions_executed": text_len, "text_positions_note": "77-token captions; the text tower runs on the positions up to the batch's last "
            "EOT (output-exact under the causal mask); algorithmic figures count the reference's full 77, executed figures the positions run",

@@ -91,6 +91,9 @@ int lpi_sim_topk_coop_bf16(const void* Q, const void* G, int n_queries, int n_ga
  * init_thr: k distinct rows reach it.  One candidate per tile keeps the pass MMA-bound. */
 int lpi_sim_topk_seed_bf16(const void* Q, const void* G, int n_queries, int n_rows, int dim, int k, float* seed_scores,
                            int* seed_idx_ws, void* stream);
+/* the pre-pass in n_chunks work items per query tile (whole waves of clusters): outputs [n_chunks, n_queries, k]; merge, then take the k-th */
+int lpi_sim_topk_seed_chunks_bf16(const void* Q, const void* G, int n_queries, int n_rows, int dim, int k, int n_chunks,
+                                  float* seed_scores, int* seed_idx_ws, void* stream);
 /* k-way merge of n_parts partial lists (chunks and/or all-gathered shards) -> [n_queries, k]. */
 int lpi_topk_merge(const float* part_scores, const int* part_idx, int n_parts, int n_queries, int k,
                    float* out_scores, int* out_idx, void* stream);
@@ -277,6 +280,25 @@ int lpi_attn_bwd_f32(const float* qkv, const float* out, const float* d_out, con
                      int H, int causal, void* stream);
 int lpi_quick_gelu_f32(const float* z, float* out, long long n, void* stream);
 int lpi_quick_gelu_bwd_f32(const float* dy, const float* z, float* out, long long n, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Exchange steps of the multi-GPU path (reference anchor: gather_features, methods/sprompt.py:38-82).
+ * One process per GPU; NCCL is resolved at run time (a copy already loaded into the process, $LPI_NCCL_LIB, or the system
+ * libnccl.so.2).  The opaque communicator is the only state the library keeps.
+ *   lpi_comm_unique_id : rank 0 fills lpi_comm_unique_id_bytes() bytes, the host ships them to the other ranks
+ *   lpi_comm_init      : collective; binds the CURRENT CUDA device of each process
+ *   lpi_comm_allgather : recv[n_ranks * bytes_per_rank] <- every rank's send[bytes_per_rank], rank-major: the ONE exchange of a sharded
+ *                        search step (each rank's [2, c, Q, k] candidate buffer, see lpi_topk_merge_recall) or of a data-parallel
+ *                        training step (the [b, 2E] image|text feature rows, see lpi_sim_infonce_fwd_bwd)
+ *   lpi_comm_allreduce_sum_f32 : the flat 5 284-float prompt gradient of a data-parallel step
+ * The Python layer uses torch.distributed for the same two collectives (same NCCL underneath); lpi_b200/comm.py wraps these entry points.
+ * ------------------------------------------------------------------------------------------------ */
+int lpi_comm_unique_id_bytes(void);
+int lpi_comm_unique_id(void* id_out);
+int lpi_comm_init(void** comm_out, int n_ranks, int rank, const void* unique_id);
+int lpi_comm_allgather(void* comm, const void* send, void* recv, long long bytes_per_rank, void* stream);
+int lpi_comm_allreduce_sum_f32(void* comm, const float* send, float* recv, long long n, void* stream);
+int lpi_comm_destroy(void* comm);
 
 #ifdef __cplusplus
 }

@@ -1520,3 +1520,10 @@ extern "C" int lpi_sim_topk_seed_bf16(const void* Q, const void* G, int n_querie
                                       int* seed_idx_ws, void* stream) {
     return sim_topk_impl(Q, G, n_queries, n_rows, dim, k, 0, 1, nullptr, 1, 1, seed_scores, seed_idx_ws, stream);
 }
+
+// The same pre-pass cut into n_chunks work items per query tile (seed_scores / seed_idx_ws [n_chunks, n_queries, k]): 98 query-tile pairs
+// on 74 clusters are 1.3 waves, 98 x 3 shorter items are 3.97.  Merge the chunk lists (lpi_topk_merge) and take the k-th entry.
+extern "C" int lpi_sim_topk_seed_chunks_bf16(const void* Q, const void* G, int n_queries, int n_rows, int dim, int k, int n_chunks,
+                                             float* seed_scores, int* seed_idx_ws, void* stream) {
+    return sim_topk_impl(Q, G, n_queries, n_rows, dim, k, 0, n_chunks, nullptr, 1, 1, seed_scores, seed_idx_ws, stream);
+}

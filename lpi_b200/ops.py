@@ -159,6 +159,7 @@ import os as _os
 
 SEED_ROWS = int(_os.environ.get("LPI_SEED_ROWS", "16384"))   # gallery rows scored first to seed the per-query thresholds of the main pass
 SEED_MIN_GALLERY = 131072    # below this the warm-up is not worth a second launch
+SEED_CHUNKED = _os.environ.get("LPI_SEED_CHUNKED", "0") != "0"  # threshold pre-pass in as many work items as fill whole waves (measured: 11.49 vs 11.52 ms at 625 k rows -- the extra merge launch eats the gain; off)
 COOP_THRESHOLDS = _os.environ.get("LPI_COOP_THR", "1") != "0"   # chunks of one launch share their per-query thresholds (see sim_topk)
 
 
@@ -193,10 +194,17 @@ def sim_topk(q: torch.Tensor, g: torch.Tensor, k: int = 10, gallery_offset: int 
             raise _lib.LpiError(f"init_thr must be [{nq}], got {tuple(init_thr.shape)}")
         thr_ptr, thr_stride = ptr(init_thr), 1
     elif seed_rows >= k:     # k-th largest per-tile maximum of the sample = the seed (-inf if the sample has fewer than k tiles)
-        seed_scores = torch.empty(1, nq, k, device=q.device, dtype=torch.float32)
-        seed_idx = torch.empty(1, nq, k, device=q.device, dtype=torch.int32)
-        call("sim_topk_seed_bf16", ptr(q), ptr(g), nq, seed_rows, dim, k, ptr(seed_scores), ptr(seed_idx), stream_ptr())
-        _count()
+        sc_ = sim_topk_chunks(nq, seed_rows) if SEED_CHUNKED else 1       # whole waves of clusters for the pre-pass too
+        seed_scores = torch.empty(sc_, nq, k, device=q.device, dtype=torch.float32)
+        seed_idx = torch.empty(sc_, nq, k, device=q.device, dtype=torch.int32)
+        if sc_ > 1:
+            call("sim_topk_seed_chunks_bf16", ptr(q), ptr(g), nq, seed_rows, dim, k, sc_, ptr(seed_scores), ptr(seed_idx), stream_ptr())
+            _count()
+            ms_, _ = topk_merge(seed_scores, seed_idx)                   # k largest tile maxima of the union of the chunks
+            seed_scores = ms_.unsqueeze(0)
+        else:
+            call("sim_topk_seed_bf16", ptr(q), ptr(g), nq, seed_rows, dim, k, ptr(seed_scores), ptr(seed_idx), stream_ptr())
+            _count()
         thr_ptr, thr_stride = C.c_void_p(seed_scores.data_ptr() + 4 * (k - 1)), k
     if out is not None:
         ps, pi = out

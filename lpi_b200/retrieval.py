@@ -159,7 +159,12 @@ def merge_recall(buf: torch.Tensor, gt_ptr: torch.Tensor, gt_idx: torch.Tensor, 
     together, 2 * c * Q * k * 4 bytes per rank) and ONE kernel that merges the world * c lists per query by (score desc, index asc)
     and counts Recall@1/5/10 per task.  -> (scores [Q,k], idx [Q,k], counts [n_tasks,4][, rank [Q]])."""
     packed = buf.unsqueeze(0)
-    if group is not None:
+    from .comm import LpiComm
+
+    if isinstance(group, LpiComm):                       # the C-ABI exchange (lpi_comm_allgather) instead of torch.distributed
+        if group.n_ranks > 1:
+            packed = group.all_gather(buf)
+    elif group is not None:
         import torch.distributed as dist
 
         world = dist.get_world_size(group)

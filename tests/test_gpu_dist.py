@@ -24,11 +24,24 @@ def _scorer_worker(rank, world, port, out):
         lo, hi = R.shard_bounds(ng, world, rank, align=256)
         shard, q, gt = S.make_gallery_shard(ng, lo, hi, nq, 512, device=f"cuda:{rank}")
         sc, ix = R.search_topk(q, shard, 10, "bf16", lo, dist.group.WORLD)
+        # the same exchange through the C ABI (lpi_comm_*): one all-gather of the packed per-chunk lists + the fused merge / recall kernel
+        from lpi_b200.comm import LpiComm
+        comm = LpiComm.from_torch_group(dist.group.WORLD)
+        nch = ops.sim_topk_chunks(nq, hi - lo)
+        buf, sv, iv = R.exchange_buffer(nch, nq, 10, f"cuda:{rank}")
+        ops.sim_topk(q, shard, 10, lo, nch, merge=False, out=(sv, iv))
+        gptr, gidx = R.gt_csr([[int(g)] for g in gt.tolist()])
+        task = torch.zeros(nq, dtype=torch.int32, device=f"cuda:{rank}")
+        sc2, ix2, counts = R.merge_recall(buf, gptr.to(sc.device), gidx.to(sc.device), task, 1, comm)
+        gsum = comm.all_reduce_sum_(torch.full((4,), float(rank + 1), device=sc.device))
+        comm_ok = bool(torch.equal(ix2, ix) and torch.equal(sc2, sc) and float(gsum[0]) == world * (world + 1) / 2 and int(counts[0, 3]) == nq)
+        torch.cuda.synchronize()
+        comm.close()
         if rank == 0:
             full, q2, _ = S.make_gallery_shard(ng, 0, ng, nq, 512, device="cuda:0")
             assert torch.equal(q, q2) and torch.equal(full[lo:hi], shard)          # sharding-independent workload
             s1, i1 = ops.sim_topk(q2, full, 10)
-            out.put(("scorer", bool(torch.equal(ix, i1) and torch.equal(sc, s1))))
+            out.put(("scorer", bool(torch.equal(ix, i1) and torch.equal(sc, s1) and comm_ok)))
     finally:
         dist.destroy_process_group()
 

@@ -155,6 +155,32 @@ def test_fused_merge_recall_equals_separate_kernels():
     assert torch.equal(v1, wv1) and torch.equal(i1, wi1) and torch.equal(c1, ops.recall_counts(wi1, ptr.cuda(), idx.cuda(), task.cuda(), 4))
 
 
+def test_lpi_comm_single_rank_roundtrip():
+    """lpi_comm_* (the C-ABI exchange steps) with one rank: NCCL is resolved at run time, all-gather / all-reduce are identities, and the
+    sharded-search tail accepts the communicator in place of a torch.distributed group."""
+    from lpi_b200.comm import LpiComm, unique_id
+
+    uid = unique_id()
+    assert len(uid) == 128
+    comm = LpiComm(1, 0, uid)
+    x = torch.arange(24, dtype=torch.int32, device="cuda").view(2, 3, 4)
+    assert torch.equal(comm.all_gather(x), x.unsqueeze(0))
+    g = torch.randn(5284, device="cuda")
+    want = g.clone()
+    assert torch.equal(comm.all_reduce_sum_(g), want)
+    gen = torch.Generator().manual_seed(5)
+    q = torch.randn(64, 512, generator=gen).bfloat16().cuda()
+    gal = torch.randn(5000, 512, generator=gen).bfloat16().cuda()
+    buf, sv, iv = R.exchange_buffer(2, 64, 10, "cuda")
+    ops.sim_topk(q, gal, 10, 0, 2, merge=False, out=(sv, iv))
+    ptr, idx = R.gt_csr([[int(i)] for i in range(64)])
+    task = torch.zeros(64, dtype=torch.int32, device="cuda")
+    a = R.merge_recall(buf, ptr.cuda(), idx.cuda(), task, 1, comm)
+    b = R.merge_recall(buf, ptr.cuda(), idx.cuda(), task, 1, None)
+    assert all(torch.equal(x_, y_) for x_, y_ in zip(a, b))
+    comm.close()
+
+
 def test_topk_rows_and_merge_ties():
     gen = torch.Generator().manual_seed(11)
     s = torch.randn(70, 4001, generator=gen)

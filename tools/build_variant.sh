@@ -10,6 +10,6 @@ for f in lpi_b200/csrc/*.cu; do
   pids+=($!)
 done
 for p in "${pids[@]}"; do wait $p; done
-nvcc -shared -gencode arch=compute_100a,code=sm_100a -o "$out" build/variant_$$/*.o
+nvcc -shared -gencode arch=compute_100a,code=sm_100a -o "$out" build/variant_$$/*.o -ldl
 rm -rf build/variant_$$
 echo "built $out"
