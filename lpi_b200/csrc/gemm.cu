@@ -846,10 +846,18 @@ struct PairCfg {
 
 enum { OP_BF16 = 0, OP_TF32 = 1, OP_F16 = 2 };      // operand type of the CTA-pair GEMM
 
-template <int MODE, int EPI, int OP, int BN_ = 256>
+// CL = CTAs per cluster: 2 (one CTA pair), or 4 in MODE_GEMM = TWO pairs working on vertically adjacent 256-row blocks of the SAME N tile.
+// The two pairs need the same weight (B) rows, so each of the four CTAs fetches only a QUARTER of the B tile and multicasts it to its
+// counterpart in the other pair: per CTA and k-block 16 KB (A) + 8 KB (B) leave L2 instead of 16 + 16.  The encoder GEMMs are bound by
+// exactly that traffic: their time follows (operand bytes read from L2 + 2 x epilogue bytes) / 12.5 TB/s on every shape
+// (profiles/r2_gemm_vs_cublas.md).  Protocol changes against CL = 2: a stage is free when the MMAs of BOTH pairs have read it (empty
+// barriers count 2 commits, multicast to all four CTAs); every pair leader still expects the bytes of its own pair's stage.
+template <int MODE, int EPI, int OP, int BN_ = 256, int CL = 2>
 __global__ void __launch_bounds__(PairCfg<MODE, BN_>::THREADS, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmArgs p) {
+    static_assert(CL == 2 || (CL == 4 && MODE == MODE_GEMM), "4-CTA clusters exist for the GEMM mode only");
     using C = PairCfg<MODE, BN_>;
+    constexpr int NPAIR = CL / 2;
     constexpr bool TF32 = OP == OP_TF32;
     constexpr bool F16 = OP == OP_F16;
     constexpr int BN = C::BN;
@@ -868,9 +876,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const uint32_t rank = cluster_ctarank();
+    const uint32_t crank = cluster_ctarank();
+    const uint32_t rank = crank & 1;                 // rank inside the CTA pair
+    const uint32_t pair = crank >> 1;                // pair inside the cluster (always 0 for CL = 2)
     const bool leader = rank == 0;
-    const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+    const int cluster_id = blockIdx.x / CL, n_clusters = gridDim.x / CL;
+    const uint16_t pair_mask = uint16_t(3u << (2 * pair)), all_mask = uint16_t((1u << CL) - 1);
     const int num_k = p.K / BKE;
     const int num_m = (p.M + BM - 1) / BM, num_mp = (num_m + 1) / 2, num_n = (p.N + BN - 1) / BN;
 
@@ -882,7 +893,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (lane == 0) {
             for (int s = 0; s < C::STAGES; ++s) {
                 mbar_init(full_bar(s), 1);       // leader's own arrive.expect_tx (bytes of both CTAs)
-                mbar_init(empty_bar(s), 1);      // multicast commit
+                mbar_init(empty_bar(s), NPAIR);  // multicast commit of every pair whose MMAs read (a multicast copy of) this stage
             }
             for (int a = 0; a < 2; ++a) {
                 mbar_init(tfull_bar(a), 1);      // multicast commit
@@ -908,7 +919,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     //        210 MB of DRAM reads for the 84 MB operand of the K = 3072 dgrad, profiles/r2_gemm_vs_cublas.md.)  This CTA owns rows
     //        (2 mp + rank) * 128
     // TOPK : item i -> (qp = i % num_mp, chunk = i / num_mp); gallery tiles [chunk * tpc, min(num_n, (chunk + 1) * tpc))
-    const int total = (MODE == MODE_GEMM) ? num_mp * num_n : num_mp * p.n_chunks;
+    //        (CL = 4: cluster tile t -> (nt = t % num_n, mq = t / num_n), pair q of the cluster owns row-block pair mp = 2 mq + q)
+    const int total = (MODE == MODE_GEMM) ? ((num_mp + NPAIR - 1) / NPAIR) * num_n : num_mp * p.n_chunks;
     // TOPK item order stays chunk-major (concurrent clusters stream the same gallery region) with cooperative thresholds too: the
     // chunk-fastest order, which lets the chunks of one query tile warm each other up from the first wave on, measured 7 % SLOWER
     // (625 k rows: 12.10 vs 11.34 ms; the exact-threshold run slows down as well, i.e. it is the lost L2 locality of the gallery stream)
@@ -920,8 +932,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             int stage = 0;
             uint32_t phase = 0, aphase = 0;
             for (int t = cluster_id; t < total; t += n_clusters) {
-                const int mp = (MODE == MODE_GEMM) ? (LPI_RASTER_N ? t / num_n : t % num_mp) : (topk_qmajor ? t / p.n_chunks : t % num_mp);
-                const int second = (MODE == MODE_GEMM) ? (LPI_RASTER_N ? t % num_n : t / num_mp) : (topk_qmajor ? t % p.n_chunks : t / num_mp);
+                const int mp = (MODE == MODE_GEMM) ? (CL == 4 ? NPAIR * (t / num_n) + int(pair) : (LPI_RASTER_N ? t / num_n : t % num_mp)) : (topk_qmajor ? t / p.n_chunks : t % num_mp);
+                const int second = (MODE == MODE_GEMM) ? ((CL == 4 || LPI_RASTER_N) ? t % num_n : t / num_mp) : (topk_qmajor ? t % p.n_chunks : t / num_mp);
                 const int m0 = (2 * mp + int(rank)) * BM;
                 int n_begin, n_end;
                 if (MODE == MODE_GEMM) { n_begin = second; n_end = second + 1; }
@@ -947,7 +959,14 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         const uint32_t sa = smem_base + C::RING_OFF + stage * C::STAGE_BYTES;
                         if (MODE == MODE_GEMM) {
                             if (!skip_a) tma_load_2d_pair(sa, &tmA, full_bar(stage), kb * BKE, m0);
-                            tma_load_2d_pair(sa + C::A_BYTES, &tmB, full_bar(stage), kb * BKE, n0);
+                            if (CL == 4) {
+                                // this CTA's quarter of the B tile (half of the half its pair-rank holds), to itself and to the CTA of the
+                                // same pair-rank in the other pair
+                                tma_load_2d_pair_mc(sa + C::A_BYTES + pair * (C::BH_BYTES / 2), &tmB, full_bar(stage), kb * BKE,
+                                                    n0 + int(pair) * (BN / 4), uint16_t(5u << rank));
+                            } else {
+                                tma_load_2d_pair(sa + C::A_BYTES, &tmB, full_bar(stage), kb * BKE, n0);
+                            }
                         } else {
                             tma_load_2d_pair(sa, &tmB, full_bar(stage), kb * BKE, n0);
                         }
@@ -963,7 +982,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0, aphase = 0;
             for (int t = cluster_id; t < total; t += n_clusters) {
-                const int second = (MODE == MODE_GEMM) ? (LPI_RASTER_N ? t % num_n : t / num_mp) : (topk_qmajor ? t % p.n_chunks : t / num_mp);
+                const int second = (MODE == MODE_GEMM) ? ((CL == 4 || LPI_RASTER_N) ? t % num_n : t / num_mp) : (topk_qmajor ? t % p.n_chunks : t / num_mp);
                 int n_begin, n_end;
                 if (MODE == MODE_GEMM) { n_begin = second; n_end = second + 1; }
                 else {
@@ -988,13 +1007,13 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                             if (TF32) umma_tf32_ss_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
                             else umma_f16_ss_pair(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
                         }
-                        umma_commit_pair(empty_bar(stage));
+                        umma_commit_pair(empty_bar(stage), all_mask);        // the stage is reusable in every CTA it was multicast to
                         if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                     }
-                    umma_commit_pair(tfull_bar(acc));
+                    umma_commit_pair(tfull_bar(acc), pair_mask);
                     if (++acc == 2) { acc = 0; acc_phase ^= 1; }
                 }
-                if (MODE == MODE_TOPK) umma_commit_pair(aempty_bar);     // every MMA reading the resident tile has retired
+                if (MODE == MODE_TOPK) umma_commit_pair(aempty_bar, pair_mask);     // every MMA reading the resident tile has retired
             }
         }
     } else {
@@ -1007,10 +1026,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         uint32_t acc_phase = 0;
         TopkState tk{reinterpret_cast<float*>(smem_gen + C::LIST_OFF), reinterpret_cast<int*>(smem_gen + C::LIST_OFF + BM * TOPK_MAX * 4),
                      r_local, p.k, 0, -INFINITY};
-        const uint32_t tempty_leader0 = mapa_u32(tempty_bar(0), 0), tempty_leader1 = mapa_u32(tempty_bar(1), 0);
+        const uint32_t tempty_leader0 = mapa_u32(tempty_bar(0), 2 * pair), tempty_leader1 = mapa_u32(tempty_bar(1), 2 * pair);
         for (int t = cluster_id; t < total; t += n_clusters) {
-            const int mp = (MODE == MODE_GEMM) ? (LPI_RASTER_N ? t / num_n : t % num_mp) : (topk_qmajor ? t / p.n_chunks : t % num_mp);
-                const int second = (MODE == MODE_GEMM) ? (LPI_RASTER_N ? t % num_n : t / num_mp) : (topk_qmajor ? t % p.n_chunks : t / num_mp);
+            const int mp = (MODE == MODE_GEMM) ? (CL == 4 ? NPAIR * (t / num_n) + int(pair) : (LPI_RASTER_N ? t / num_n : t % num_mp)) : (topk_qmajor ? t / p.n_chunks : t % num_mp);
+                const int second = (MODE == MODE_GEMM) ? ((CL == 4 || LPI_RASTER_N) ? t % num_n : t / num_mp) : (topk_qmajor ? t % p.n_chunks : t / num_mp);
             const int m0 = (2 * mp + int(rank)) * BM;
             const int row = m0 + r_local;
             int n_begin, n_end;
@@ -1228,9 +1247,9 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs
     return 0;
 }
 
-template <int MODE, int EPI, int OP, int BN = 256>
+template <int MODE, int EPI, int OP, int BN = 256, int CL = 2>
 static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, int n_clusters, cudaStream_t st) {
-    auto kern = gemm_pair_kernel<MODE, EPI, OP, BN>;
+    auto kern = gemm_pair_kernel<MODE, EPI, OP, BN, CL>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, PairCfg<MODE, BN>::SMEM_BYTES);
@@ -1238,48 +1257,68 @@ static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
         configured = true;
     }
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(2 * n_clusters);
+    cfg.gridDim = dim3(CL * n_clusters);
     cfg.blockDim = dim3(PairCfg<MODE, BN>::THREADS);
     cfg.dynamicSmemBytes = PairCfg<MODE, BN>::SMEM_BYTES;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.x = CL;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
+    if (CL > 2) {
+        // the kernel is persistent (one CTA per SM): a grid larger than what can be co-resident would run in two rounds.  4-CTA clusters
+        // must sit inside one GPC, so fewer than sms / 4 of them may fit (GPCs with a TPC count that is not a multiple of two)
+        static int max_clusters = 0;
+        if (!max_clusters) {
+            int n = 0;
+            cudaLaunchConfig_t probe = cfg;
+            probe.gridDim = dim3(CL * (num_sms() / CL));
+            if (cudaOccupancyMaxActiveClusters(&n, kern, &probe) != cudaSuccess || n < 1) n = num_sms() / CL;
+            max_clusters = n;
+            if (getenv("LPI_GEMM_VERBOSE")) fprintf(stderr, "[lpi_b200] %d-CTA clusters co-resident: %d (of %d SMs)\n", CL, n, num_sms());
+        }
+        if (n_clusters > max_clusters) cfg.gridDim = dim3(CL * max_clusters);
+    }
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, a);
     if (e != cudaSuccess) return set_error(LPI_ERR_CUDA, "pair gemm launch: %s", cudaGetErrorString(e));
     return 0;
 }
 
-template <int OP, int BN>
+template <int OP, int BN, int CL>
 static int launch_pair_epi_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, int n_clusters, cudaStream_t st) {
     constexpr bool TF32 = OP == OP_TF32;
     constexpr int OPH = TF32 ? OP_BF16 : OP;          // the 16-bit-only epilogues are never instantiated for TF32 operands
     switch (a.epi) {
-        case EPI_BIAS_BF16: return launch_pair<MODE_GEMM, EPI_BIAS_BF16, OP, BN>(tmA, tmB, a, n_clusters, st);
-        case EPI_BIAS_RESID_F32: return launch_pair<MODE_GEMM, EPI_BIAS_RESID_F32, OP, BN>(tmA, tmB, a, n_clusters, st);
-        case EPI_F32: return launch_pair<MODE_GEMM, EPI_F32, OP, BN>(tmA, tmB, a, n_clusters, st);
-        case EPI_BF16: return launch_pair<MODE_GEMM, EPI_BF16, OP, BN>(tmA, tmB, a, n_clusters, st);
-        case EPI_BIAS_GELU_BF16: if (!TF32) return launch_pair<MODE_GEMM, EPI_BIAS_GELU_BF16, OPH, BN>(tmA, tmB, a, n_clusters, st); break;
-        case EPI_DGELU_BF16: if (!TF32) return launch_pair<MODE_GEMM, EPI_DGELU_BF16, OPH, BN>(tmA, tmB, a, n_clusters, st); break;
-        case EPI_BIAS_F32: if (!TF32) return launch_pair<MODE_GEMM, EPI_BIAS_F32, OPH, BN>(tmA, tmB, a, n_clusters, st); break;
-        case EPI_ACC_F32: if (!TF32) return launch_pair<MODE_GEMM, EPI_ACC_F32, OPH, BN>(tmA, tmB, a, n_clusters, st); break;
-        case EPI_BIAS_GELU_F32: if (TF32 && BN == 256) return launch_pair<MODE_GEMM, EPI_BIAS_GELU_F32, OP_TF32, 256>(tmA, tmB, a, n_clusters, st); break;
-        case EPI_DGELU_F32: if (TF32 && BN == 256) return launch_pair<MODE_GEMM, EPI_DGELU_F32, OP_TF32, 256>(tmA, tmB, a, n_clusters, st); break;
+        case EPI_BIAS_BF16: return launch_pair<MODE_GEMM, EPI_BIAS_BF16, OP, BN, CL>(tmA, tmB, a, n_clusters, st);
+        case EPI_BIAS_RESID_F32: return launch_pair<MODE_GEMM, EPI_BIAS_RESID_F32, OP, BN, CL>(tmA, tmB, a, n_clusters, st);
+        case EPI_F32: return launch_pair<MODE_GEMM, EPI_F32, OP, BN, CL>(tmA, tmB, a, n_clusters, st);
+        case EPI_BF16: return launch_pair<MODE_GEMM, EPI_BF16, OP, BN, CL>(tmA, tmB, a, n_clusters, st);
+        case EPI_BIAS_GELU_BF16: if (!TF32) return launch_pair<MODE_GEMM, EPI_BIAS_GELU_BF16, OPH, BN, CL>(tmA, tmB, a, n_clusters, st); break;
+        case EPI_DGELU_BF16: if (!TF32) return launch_pair<MODE_GEMM, EPI_DGELU_BF16, OPH, BN, CL>(tmA, tmB, a, n_clusters, st); break;
+        case EPI_BIAS_F32: if (!TF32) return launch_pair<MODE_GEMM, EPI_BIAS_F32, OPH, BN, CL>(tmA, tmB, a, n_clusters, st); break;
+        case EPI_ACC_F32: if (!TF32) return launch_pair<MODE_GEMM, EPI_ACC_F32, OPH, BN, CL>(tmA, tmB, a, n_clusters, st); break;
+        case EPI_BIAS_GELU_F32: if (TF32 && BN == 256 && CL == 2) return launch_pair<MODE_GEMM, EPI_BIAS_GELU_F32, OP_TF32, 256, 2>(tmA, tmB, a, n_clusters, st); break;
+        case EPI_DGELU_F32: if (TF32 && BN == 256 && CL == 2) return launch_pair<MODE_GEMM, EPI_DGELU_F32, OP_TF32, 256, 2>(tmA, tmB, a, n_clusters, st); break;
     }
-    return set_error(LPI_ERR_ARG, "epilogue %d is not available for this operand type / tile width %d", a.epi, BN);
+    return set_error(LPI_ERR_ARG, "epilogue %d is not available for this operand type / tile width %d / cluster %d", a.epi, BN, CL);
 }
 
 template <int OP>
-static int launch_pair_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, int n_clusters, int bn, cudaStream_t st) {
-    if (OP != OP_TF32) {                              // narrower cluster tiles exist for the 16-bit operand types only
-        if (bn == 192) return launch_pair_epi_bn<OP == OP_TF32 ? OP_BF16 : OP, 192>(tmA, tmB, a, n_clusters, st);
-        if (bn == 128) return launch_pair_epi_bn<OP == OP_TF32 ? OP_BF16 : OP, 128>(tmA, tmB, a, n_clusters, st);
+static int launch_pair_epi(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmArgs& a, int n_clusters, int bn, int cl, cudaStream_t st) {
+    if (OP != OP_TF32) {                              // narrower cluster tiles and 4-CTA clusters exist for the 16-bit operand types only
+        constexpr int O16 = OP == OP_TF32 ? OP_BF16 : OP;
+        if (cl == 4) {
+            if (bn == 256) return launch_pair_epi_bn<O16, 256, 4>(tmA, tmB, a, n_clusters, st);
+            if (bn == 192) return launch_pair_epi_bn<O16, 192, 4>(tmA, tmB, a, n_clusters, st);
+            if (bn == 128) return launch_pair_epi_bn<O16, 128, 4>(tmA, tmB, a, n_clusters, st);
+        }
+        if (bn == 192) return launch_pair_epi_bn<O16, 192, 2>(tmA, tmB, a, n_clusters, st);
+        if (bn == 128) return launch_pair_epi_bn<O16, 128, 2>(tmA, tmB, a, n_clusters, st);
     }
-    return launch_pair_epi_bn<OP, 256>(tmA, tmB, a, n_clusters, st);
+    return launch_pair_epi_bn<OP, 256, 2>(tmA, tmB, a, n_clusters, st);
 }
 
 template <int BN>
@@ -1332,26 +1371,40 @@ static int gemm_entry(int op, const void* A, const void* B, int M, int N, int K,
     int bn = tile_n;
     const int sms = num_sms();
     // tile_n: 0 = automatic; 128 / 256 = 1-CTA 128 x tile_n tiles; 512 (= 1256) / 1192 / 1128 = CTA-pair 256 x {256, 192, 128} cluster tiles
-    int pair_bn = 0;
+    int pair_bn = 0, cl = 2;
+    // 4-CTA clusters (B tile multicast between two CTA pairs) are OPT-IN (LPI_GEMM_CLUSTER4=1, or tile_n 2xxx): correct on every shape
+    // and ~10 % faster per SM, but only 33 such clusters (132 of 148 SMs) can be co-resident on a B200 -- 4-CTA clusters must sit
+    // inside one GPC -- which cancels the gain: qkv 43.4 vs 42.0 us, K = 3072 dgrad 64.3 vs 56.0 us (profiles/r2_gemm_cluster4.txt)
+    static int cluster4 = -1;
+    if (cluster4 < 0) {
+        const char* e = getenv("LPI_GEMM_CLUSTER4");
+        cluster4 = (e && e[0] == '1') ? 1 : 0;
+    }
+    const long mp_all = ((M + BM - 1) / BM + 1) / 2;
     if (bn == 0) {
         // CTA-pair tiles whenever N allows: they measured at or above the 1-CTA tiles on every encoder shape
-        // (profiles/r2_gemm_microbench.txt).  The cluster tile width is the one that wastes least of the last wave: full waves of 74
-        // clusters x a per-tile efficiency (a narrower tile streams more operand bytes per FLOP).
-        const long mp = ((M + BM - 1) / BM + 1) / 2;
+        // (profiles/r2_gemm_microbench.txt).  Cluster tile width and cluster size are the combination that wastes least of the last wave
+        // (full waves of 74 pair clusters / 37 four-CTA clusters) x a per-tile efficiency: a narrower tile streams more operand bytes per
+        // FLOP, a 4-CTA cluster (B multicast to two pairs) 25 % fewer.
         double best = 0.0;
         const int cand[3] = {256, 192, 128};
         const double weight[3] = {1.0, 0.96, 0.88};
-        for (int i = 0; i < 3; ++i) {
-            if (N % cand[i] || (tf32 && cand[i] != 256)) continue;
-            const long tiles = mp * (N / cand[i]), cl = sms / 2;
-            const double eff = double(tiles) / double(((tiles + cl - 1) / cl) * cl) * weight[i];
-            if (eff > best + 1e-9) { best = eff; pair_bn = cand[i]; }
+        for (int c4 = 0; c4 < 2; ++c4) {
+            if (c4 && (tf32 || !cluster4 || mp_all < 4)) continue;
+            for (int i = 0; i < 3; ++i) {
+                if (N % cand[i] || (tf32 && cand[i] != 256)) continue;
+                const long tiles = (c4 ? (mp_all + 1) / 2 : mp_all) * (N / cand[i]), ncl = c4 ? sms / 4 : sms / 2;
+                const double eff = double(tiles) / double(((tiles + ncl - 1) / ncl) * ncl) * weight[i] * (c4 ? 1.10 : 1.0);
+                if (eff > best + 1e-9) { best = eff; pair_bn = cand[i]; cl = c4 ? 4 : 2; }
+            }
         }
         if (!pair_bn) bn = 128;
     } else if (bn == 512 || bn == 1256) pair_bn = 256;
     else if (bn == 1192) pair_bn = 192;
     else if (bn == 1128) pair_bn = 128;
-    else if (bn != 128 && bn != 256) return set_error(LPI_ERR_ARG, "gemm: tile_n must be 0, 128, 256 (1-CTA) or 512 / 1192 / 1128 (CTA pair)");
+    else if (bn == 2256 || bn == 2192 || bn == 2128) { pair_bn = bn - 2000; cl = 4; }
+    else if (bn != 128 && bn != 256) return set_error(LPI_ERR_ARG, "gemm: tile_n must be 0, 128, 256 (1-CTA), 512 / 1192 / 1128 (CTA pair) or 2256 / 2192 / 2128 (two pairs, 4-CTA cluster)");
+    if (cl == 4 && tf32) return set_error(LPI_ERR_ARG, "gemm_tf32: 4-CTA clusters are built for the 16-bit operand types only");
     const bool pair = pair_bn != 0;
     if (pair && tf32 && pair_bn != 256) return set_error(LPI_ERR_ARG, "gemm_tf32: only the 256-wide CTA-pair tile is built");
     if (N % (pair ? pair_bn : bn)) return set_error(LPI_ERR_ARG, "gemm: N=%d not a multiple of the tile width (tile_n=%d)", N, tile_n);
@@ -1359,7 +1412,7 @@ static int gemm_entry(int op, const void* A, const void* B, int M, int N, int K,
     const CUtensorMapDataType dt = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : (op == OP_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
     const int eb = tf32 ? 4 : 2;
     if (int rc = make_tmap_2d(&tmA, A, dt, eb, M, K, K, BM, bke)) return rc;
-    if (int rc = make_tmap_2d(&tmB, B, dt, eb, N, K, K, pair ? pair_bn / 2 : bn, bke)) return rc;
+    if (int rc = make_tmap_2d(&tmB, B, dt, eb, N, K, K, pair ? pair_bn / cl : bn, bke)) return rc;      // box = what ONE CTA fetches of the B tile
     GemmArgs a{};
     a.M = M; a.N = N; a.K = K; a.epi = epi; a.ldo = ldo;
     {
@@ -1391,11 +1444,12 @@ static int gemm_entry(int op, const void* A, const void* B, int M, int N, int K,
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (pair) {
-        const long ctiles = long(((M + BM - 1) / BM + 1) / 2) * (N / pair_bn);
-        const int n_clusters = int(ctiles < sms / 2 ? ctiles : sms / 2);
-        return tf32 ? launch_pair_epi<OP_TF32>(tmA, tmB, a, n_clusters, pair_bn, st)
-                    : (op == OP_F16 ? launch_pair_epi<OP_F16>(tmA, tmB, a, n_clusters, pair_bn, st)
-                                    : launch_pair_epi<OP_BF16>(tmA, tmB, a, n_clusters, pair_bn, st));
+        const long ctiles = (cl == 4 ? (mp_all + 1) / 2 : mp_all) * (N / pair_bn);
+        const long max_cl = sms / cl;
+        const int n_clusters = int(ctiles < max_cl ? ctiles : max_cl);
+        return tf32 ? launch_pair_epi<OP_TF32>(tmA, tmB, a, n_clusters, pair_bn, cl, st)
+                    : (op == OP_F16 ? launch_pair_epi<OP_F16>(tmA, tmB, a, n_clusters, pair_bn, cl, st)
+                                    : launch_pair_epi<OP_BF16>(tmA, tmB, a, n_clusters, pair_bn, cl, st));
     }
     if (op == OP_F16) return set_error(LPI_ERR_UNSUPPORTED, "gemm_f16: CTA-pair tiles only (tile_n 0 / 512 / 1192 / 1128)");
     const long tiles = long((M + BM - 1) / BM) * (N / bn);
@@ -1420,7 +1474,7 @@ extern "C" int lpi_gemm_f16(const void* A, const void* B, int M, int N, int K, i
                             void* out2, const void* aux, int ldo, int tile_n, void* stream) {
     if (epi == EPI_BIAS_GELU_F32 || epi == EPI_DGELU_F32)
         return set_error(LPI_ERR_ARG, "gemm_f16: epilogue %d is only available for TF32 operands", epi);
-    if (tile_n == 128 || tile_n == 256) return set_error(LPI_ERR_ARG, "gemm_f16: only the CTA-pair tiles (tile_n 0 / 512 / 1192 / 1128) are built");
+    if (tile_n == 128 || tile_n == 256) return set_error(LPI_ERR_ARG, "gemm_f16: only the CTA-pair tiles (tile_n 0 / 512 / 1192 / 1128 / 2256 / 2192 / 2128) are built");
     return gemm_entry(OP_F16, A, B, M, N, K, epi, bias, resid, out, out2, aux, ldo, tile_n, stream);
 }
 

@@ -205,6 +205,15 @@ __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst_smem, const CUtens
         ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1)
         : "memory");
 }
+// The same load MULTICAST to every CTA of `cta_mask` (cluster ranks): the box lands at the same CTA-relative offset in each destination
+// and its bytes complete on the pair-leader barrier of each destination (CUTLASS SM100_TMA_2SM_LOAD_MULTICAST) -- one L2 read feeds the
+// two CTA pairs of a 4-CTA cluster that need the same operand rows.
+__device__ __forceinline__ void tma_load_2d_pair_mc(uint32_t dst_smem, const CUtensorMap* m, uint32_t bar, int c0, int c1, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
+        ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar & kPeerBitMask), "h"(cta_mask), "r"(c0), "r"(c1)
+        : "memory");
+}
 template <int kCols>
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem) {   // one warp in EACH CTA of the pair, same dst offset
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "n"(kCols) : "memory");
@@ -232,9 +241,9 @@ __device__ __forceinline__ void umma_tf32_ss_pair(uint32_t tmem_d, uint64_t desc
         : "memory");
 }
 // completion of all MMAs issued so far arrives on the mbarrier at this offset in BOTH CTAs of the pair
-__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t cta_mask = 3) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(bar), "h"(uint16_t(3)) : "memory");
+                 ::"r"(bar), "h"(cta_mask) : "memory");
 }
 
 // ---------------------------------------------------------------- misc

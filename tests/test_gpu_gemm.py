@@ -53,9 +53,9 @@ def _case(M, N, K, epi, tile_n, seed=0, half=torch.bfloat16):
 
 @pytest.mark.parametrize("M,N,K", [(100, 128, 64), (300, 512, 512), (4928, 1536, 512), (13632, 2304, 768),
                                    (13632, 768, 3072), (1, 128, 64)])
-@pytest.mark.parametrize("tile_n", [0, 128, 256, 512, 1192, 1128])
+@pytest.mark.parametrize("tile_n", [0, 128, 256, 512, 1192, 1128, 2256, 2192, 2128])
 def test_gemm_shapes(M, N, K, tile_n):
-    if tile_n and N % {128: 128, 256: 256, 512: 256, 1192: 192, 1128: 128}[tile_n]:
+    if tile_n and N % {128: 128, 256: 256, 512: 256, 1192: 192, 1128: 128, 2256: 256, 2192: 192, 2128: 128}[tile_n]:
         pytest.skip("N not a multiple of the tile")
     _case(M, N, K, ops.EPI_F32, tile_n)
 
@@ -69,10 +69,11 @@ def test_gemm_epilogues(epi):
 
 
 @pytest.mark.parametrize("epi", range(8))
-@pytest.mark.parametrize("tile_n", [1192, 1128])
+@pytest.mark.parametrize("tile_n", [1192, 1128, 2256, 2192, 2128])
 def test_gemm_narrow_pair_tiles(epi, tile_n):
     """CTA-pair kernel with 256 x 192 / 256 x 128 cluster tiles (picked automatically when 256-wide tiles would leave the last wave
-    mostly empty, e.g. N = 768 at B = 64): every epilogue, ragged M, both 16-bit operand types."""
+    mostly empty, e.g. N = 768 at B = 64) and the 4-CTA clusters (2xxx: two pairs on adjacent row blocks of one N tile, the B tile
+    multicast between them): every epilogue, ragged M (odd numbers of row blocks and of block pairs), both 16-bit operand types."""
     _case(1000, 768, 768, epi, tile_n, seed=7)
     _case(13632, 768, 3072, epi, tile_n, seed=8)
     _case(2496, 1536, 512, epi, tile_n, seed=9, half=torch.float16)
