@@ -836,7 +836,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--gallery", type=int, default=5_000_000)
     ap.add_argument("--queries", type=int, default=25_000)
-    ap.add_argument("--e2e-chunks", type=int, default=8, help="host->device pipeline depth of the e2e leg (gallery shard copied in this many pieces)")
+    ap.add_argument("--e2e-chunks", type=int, default=16, help="host->device pipeline depth of the e2e leg (gallery shard copied in this many pieces)")
     ap.add_argument("--e2e-streams", type=int, default=1, help="copy streams the e2e leg spreads its host->device chunks over")
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs: no cpu_baseline / reference legs")
     ap.add_argument("--skip-train", action="store_true", help="skip the secondary train pairs/s leg")

@@ -120,41 +120,63 @@ __global__ void clip_dlogits_kernel(const float* __restrict__ S, const float* __
 // BASELINE configs[2] (64 ... 512), a few ms at n = 4096.
 namespace cg = cooperative_groups;
 
+// The opposite feature matrix is walked in tiles of TJ rows staged in shared memory by the whole block (coalesced float4 loads, all in
+// flight at once): a warp that fetched each row itself paid one L2 round trip per score (130 us at n = 64 for microseconds of math).
 template <int NV>          // feature width E = 32 * NV' with NV' <= NV
 __global__ void __launch_bounds__(256)
 sim_infonce_kernel(const float* __restrict__ img, const float* __restrict__ txt, int n, int E, float scale, float weight, int row0, int n_local,
                    float* __restrict__ lse, float* __restrict__ terms, float* __restrict__ loss, float* __restrict__ logits,
-                   float* __restrict__ d_img, float* __restrict__ d_txt) {
+                   float* __restrict__ d_img, float* __restrict__ d_txt, int TJ) {
+    extern __shared__ float tile[];            // [TJ][E]
     cg::grid_group grid = cg::this_grid();
-    const int lane = threadIdx.x & 31;
-    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int nv = E >> 5;
-    // ---- phase 1: row log-sum-exps (tasks [0, n): rows of I against all of T) and column ones (tasks [n, 2n): rows of T against all of I)
-    for (int task = gw; task < 2 * n; task += nwarps) {
-        const bool col = task >= n;
-        const int idx = col ? task - n : task;
-        const float* A = (col ? txt : img) + size_t(idx) * E;
+    auto stage = [&](const float* Bm, int j0) {        // rows [j0, j0 + TJ) of Bm -> tile (rows past n: zeros)
+        __syncthreads();
+        const int n4 = TJ * E / 4;
+        for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+            const int r = (i * 4) / E;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (j0 + r < n) v = *reinterpret_cast<const float4*>(Bm + size_t(j0) * E + size_t(i) * 4);
+            reinterpret_cast<float4*>(tile)[i] = v;
+        }
+        __syncthreads();
+    };
+    // ---- phase 1: row log-sum-exps (side 0: rows of I against all of T) and column ones (side 1: rows of T against all of I);
+    //      a block works on 8 consecutive rows of ONE side, so all its warps walk the same opposite matrix
+    const int bps = (n + 7) >> 3;
+    for (int bt = blockIdx.x; bt < 2 * bps; bt += gridDim.x) {
+        const bool col = bt >= bps;
+        const int idx = (bt - (col ? bps : 0)) * 8 + warp;
+        const bool valid = idx < n;
+        const float* A = (col ? txt : img) + size_t(valid ? idx : 0) * E;
         const float* Bm = col ? img : txt;
         float a[NV];
 #pragma unroll
-        for (int t = 0; t < NV; ++t) a[t] = t < nv ? A[lane + 32 * t] : 0.f;
+        for (int t = 0; t < NV; ++t) a[t] = (t < nv && valid) ? A[lane + 32 * t] : 0.f;
         float m = -CUDART_INF_F, l = 0.f, diag = 0.f;
-        for (int j = 0; j < n; ++j) {
-            const float* b = Bm + size_t(j) * E;
-            float p = 0.f;
+        for (int j0 = 0; j0 < n; j0 += TJ) {
+            stage(Bm, j0);
+            const int jn = min(TJ, n - j0);
+            if (valid) {
+                for (int jj = 0; jj < jn; ++jj) {
+                    const float* b = tile + jj * E;
+                    float p = 0.f;
 #pragma unroll
-            for (int t = 0; t < NV; ++t) if (t < nv) p = fmaf(a[t], b[lane + 32 * t], p);
-            const float sc = scale * warp_sum(p);
-            const float mn = fmaxf(m, sc);
-            l = l * expf(m - mn) + expf(sc - mn);
-            m = mn;
-            if (j == idx) diag = sc;
-            if (!col && logits && lane == 0) logits[size_t(idx) * n + j] = sc;
+                    for (int t = 0; t < NV; ++t) if (t < nv) p = fmaf(a[t], b[lane + 32 * t], p);
+                    const float sc = scale * warp_sum(p);
+                    const float mn = fmaxf(m, sc);
+                    l = l * expf(m - mn) + expf(sc - mn);
+                    m = mn;
+                    if (j0 + jj == idx) diag = sc;
+                    if (!col && logits && lane == 0) logits[size_t(idx) * n + j0 + jj] = sc;
+                }
+            }
         }
-        if (lane == 0) {
+        if (valid && lane == 0) {
             const float v = m + logf(l);
-            lse[task] = v;
-            terms[task] = v - diag;
+            lse[(col ? n : 0) + idx] = v;
+            terms[(col ? n : 0) + idx] = v - diag;
         }
     }
     grid.sync();
@@ -164,7 +186,7 @@ sim_infonce_kernel(const float* __restrict__ img, const float* __restrict__ txt,
         float s = 0.f;
         for (int i = threadIdx.x; i < 2 * n; i += blockDim.x) s += terms[i];
         s = warp_sum(s);
-        if (lane == 0) red[threadIdx.x >> 5] = s;
+        if (lane == 0) red[warp] = s;
         __syncthreads();
         if (threadIdx.x == 0) {
             float v = 0.f;
@@ -172,36 +194,46 @@ sim_infonce_kernel(const float* __restrict__ img, const float* __restrict__ txt,
             *loss = weight * v / (2.f * n);
         }
     }
-    // ---- phase 3: gradients of the local rows (tasks [0, n_local): dI rows; [n_local, 2 n_local): dT rows); scores are recomputed
+    // ---- phase 3: gradients of the local rows (side 0: dI rows, side 1: dT rows); scores are recomputed from the staged tiles
     if (d_img == nullptr && d_txt == nullptr) return;
     const float w2 = weight / (2.f * n);
-    for (int task = gw; task < 2 * n_local; task += nwarps) {
-        const bool col = task >= n_local;
-        const int idx = row0 + (col ? task - n_local : task);
+    const int bpl = (n_local + 7) >> 3;
+    for (int bt = blockIdx.x; bt < 2 * bpl; bt += gridDim.x) {
+        const bool col = bt >= bpl;
+        const int loc = (bt - (col ? bpl : 0)) * 8 + warp;
         float* out = col ? d_txt : d_img;
-        if (!out) continue;
+        const bool valid = loc < n_local && out != nullptr;
+        const int idx = row0 + (loc < n_local ? loc : 0);
         const float* A = (col ? txt : img) + size_t(idx) * E;
         const float* Bm = col ? img : txt;
-        const float own = lse[col ? n + idx : idx];              // LSE of this row (row side) / column (column side)
+        const float own = lse[(col ? n : 0) + idx];              // LSE of this row (row side) / column (column side)
         const float* other = col ? lse : lse + n;                // LSEs of the opposite side, indexed by j
         float a[NV], acc[NV];
 #pragma unroll
-        for (int t = 0; t < NV; ++t) { a[t] = t < nv ? A[lane + 32 * t] : 0.f; acc[t] = 0.f; }
-        for (int j = 0; j < n; ++j) {
-            const float* b = Bm + size_t(j) * E;
-            float bv[NV], p = 0.f;
+        for (int t = 0; t < NV; ++t) { a[t] = (t < nv && valid) ? A[lane + 32 * t] : 0.f; acc[t] = 0.f; }
+        for (int j0 = 0; j0 < n; j0 += TJ) {
+            stage(Bm, j0);
+            const int jn = min(TJ, n - j0);
+            if (valid) {
+                for (int jj = 0; jj < jn; ++jj) {
+                    const float* b = tile + jj * E;
+                    float bv[NV], p = 0.f;
 #pragma unroll
-            for (int t = 0; t < NV; ++t) { bv[t] = t < nv ? b[lane + 32 * t] : 0.f; p = fmaf(a[t], bv[t], p); }
-            const float sc = scale * warp_sum(p);
-            float g = expf(sc - own) + expf(sc - other[j]);
-            if (j == idx) g -= 2.f;
-            g *= w2;
+                    for (int t = 0; t < NV; ++t) { bv[t] = t < nv ? b[lane + 32 * t] : 0.f; p = fmaf(a[t], bv[t], p); }
+                    const float sc = scale * warp_sum(p);
+                    float g = expf(sc - own) + expf(sc - other[j0 + jj]);
+                    if (j0 + jj == idx) g -= 2.f;
+                    g *= w2;
 #pragma unroll
-            for (int t = 0; t < NV; ++t) acc[t] = fmaf(g, bv[t], acc[t]);
+                    for (int t = 0; t < NV; ++t) acc[t] = fmaf(g, bv[t], acc[t]);
+                }
+            }
         }
-        float* o = out + size_t(col ? task - n_local : task) * E;
+        if (valid) {
+            float* o = out + size_t(loc) * E;
 #pragma unroll
-        for (int t = 0; t < NV; ++t) if (t < nv) o[lane + 32 * t] = scale * acc[t];
+            for (int t = 0; t < NV; ++t) if (t < nv) o[lane + 32 * t] = scale * acc[t];
+        }
     }
 }
 
@@ -385,22 +417,26 @@ extern "C" int lpi_sim_infonce_fwd_bwd(const float* img_f, const float* txt_f, i
     if (row0 < 0 || n_local < 0 || row0 + n_local > n) return set_error(LPI_ERR_ARG, "sim_infonce: local rows [%d, %d) outside [0, %d)", row0, row0 + n_local, n);
     if (!lse_ws || !terms_ws || !loss_out) return set_error(LPI_ERR_ARG, "sim_infonce: workspace / loss pointer missing");
     auto kern = (E <= 512) ? sim_infonce_kernel<16> : sim_infonce_kernel<32>;
+    int TJ = 16384 / E;                                          // 64 KB of staged rows per block
+    if (TJ > 32) TJ = 32;
+    const int smem = TJ * E * int(sizeof(float));
     static int max_blocks[2] = {0, 0};
     const int slot = E <= 512 ? 0 : 1;
     if (!max_blocks[slot]) {
         int per_sm = 0, dev = 0, sms = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0) != cudaSuccess || per_sm < 1)
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024) != cudaSuccess)
+            return set_error(LPI_ERR_CUDA, "sim_infonce: cudaFuncSetAttribute failed");
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 64 * 1024) != cudaSuccess || per_sm < 1)
             return set_error(LPI_ERR_CUDA, "sim_infonce: occupancy query failed");
         max_blocks[slot] = per_sm * sms;                         // a cooperative grid must be co-resident
     }
-    const long warps = 2L * n;
-    int grid = int((warps + 7) / 8);
+    int grid = 2 * ((n + 7) / 8);                                // one block per 8 rows of one side
     if (grid > max_blocks[slot]) grid = max_blocks[slot];
     if (grid < 1) grid = 1;
-    void* args[] = {&img_f, &txt_f, &n, &E, &scale, &weight, &row0, &n_local, &lse_ws, &terms_ws, &loss_out, &logits_out, &d_img, &d_txt};
-    cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kern), dim3(grid), dim3(256), args, 0, static_cast<cudaStream_t>(stream));
+    void* args[] = {&img_f, &txt_f, &n, &E, &scale, &weight, &row0, &n_local, &lse_ws, &terms_ws, &loss_out, &logits_out, &d_img, &d_txt, &TJ};
+    cudaError_t e = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kern), dim3(grid), dim3(256), args, size_t(smem), static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return set_error(LPI_ERR_CUDA, "sim_infonce: cooperative launch: %s", cudaGetErrorString(e));
     return LPI_OK;
 }

@@ -161,6 +161,10 @@ SEED_ROWS = int(_os.environ.get("LPI_SEED_ROWS", "16384"))   # gallery rows scor
 SEED_MIN_GALLERY = 131072    # below this the warm-up is not worth a second launch
 SEED_CHUNKED = _os.environ.get("LPI_SEED_CHUNKED", "0") != "0"  # threshold pre-pass in as many work items as fill whole waves (measured: 11.49 vs 11.52 ms at 625 k rows -- the extra merge launch eats the gain; off)
 COOP_THRESHOLDS = _os.environ.get("LPI_COOP_THR", "1") != "0"   # chunks of one launch share their per-query thresholds (see sim_topk)
+# ... for shards up to this many rows: the sharing removes ~0.6 ms of list warm-up per launch (5 % of a 625 k-row shard, nothing measurable
+# at 5 M rows) but lets the clusters drift apart in the gallery stream, which costs L2 hits (5 M rows: 70 GB of DRAM reads with, 37-41 GB
+# without; profiles/r2_scorer_traffic.md)
+COOP_MAX_ROWS = int(_os.environ.get("LPI_COOP_MAX_ROWS", "2000000"))
 
 
 def sim_topk(q: torch.Tensor, g: torch.Tensor, k: int = 10, gallery_offset: int = 0, n_chunks: int = 0,
@@ -216,7 +220,7 @@ def sim_topk(q: torch.Tensor, g: torch.Tensor, k: int = 10, gallery_offset: int 
         ps = torch.empty(n_chunks, nq, k, device=q.device, dtype=torch.float32)
         pi = torch.empty(n_chunks, nq, k, device=q.device, dtype=torch.int32)
     if coop is None:
-        coop = COOP_THRESHOLDS and n_chunks > 1 and dim <= 512
+        coop = COOP_THRESHOLDS and n_chunks > 1 and dim <= 512 and ng <= COOP_MAX_ROWS
     if coop:
         if init_thr is not None:
             shared = init_thr.clone()
