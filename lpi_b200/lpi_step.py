@@ -198,8 +198,32 @@ class GraphedTrainStep:
         self.opt.step(r["grads"])
         return r
 
+    def prefetch(self, images: torch.Tensor, tokens: torch.Tensor) -> None:
+        """Starts the host -> device copy of the NEXT batch (pinned host tensors of the captured shapes) on a copy stream into a staging
+        buffer, so that it overlaps the step that is running; the following step() picks the staged batch up with a device-to-device
+        copy (38 MB at HBM speed instead of at PCIe speed on the critical path)."""
+        if getattr(self, "_stage", None) is None:
+            self._stage = (torch.empty_like(self.images), torch.empty_like(self.tokens))
+            self._copy_stream = torch.cuda.Stream(device=self.images.device)
+            self._staged = None
+        cs = self._copy_stream
+        cs.wait_stream(torch.cuda.current_stream())          # the previous step() has consumed the staging buffers
+        with torch.cuda.stream(cs):
+            self._stage[0].copy_(images, non_blocking=True)
+            self._stage[1].copy_(tokens, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(cs)
+        self._staged = ev
+
     def step(self, images: Optional[torch.Tensor] = None, tokens: Optional[torch.Tensor] = None) -> Dict:
-        """Replays the captured step (optionally on a new batch of the captured shape); returns the captured result tensors."""
+        """Replays the captured step (optionally on a new batch of the captured shape, or on the batch staged by prefetch()); returns the
+        captured result tensors."""
+        staged = getattr(self, "_staged", None)
+        if images is None and tokens is None and staged is not None:
+            torch.cuda.current_stream().wait_event(staged)
+            self.images.copy_(self._stage[0], non_blocking=True)
+            self.tokens.copy_(self._stage[1], non_blocking=True)
+            self._staged = None
         if images is not None:
             self.images.copy_(images, non_blocking=True)
         if tokens is not None:

@@ -166,6 +166,13 @@ def test_graphed_train_step_equals_eager(engines):
     ra = lpi_step.train_step(vision, text, fa, images2, tokens, 1 / 0.07, text_len=text_len)
     rb = g.step(images2)
     assert abs(float(ra["losses"]["base_loss"]) - float(rb["losses"]["base_loss"])) < 1e-6
+    # a batch staged from pinned host memory on the copy stream (prefetch) is what the next step() runs on
+    oa.step(ra["grads"])
+    images3 = S.make_images(4, 10)
+    ra = lpi_step.train_step(vision, text, fa, images3.cuda(), tokens, 1 / 0.07, text_len=text_len)
+    g.prefetch(images3.pin_memory(), tokens.cpu().pin_memory())
+    rb = g.step()
+    assert abs(float(ra["losses"]["base_loss"]) - float(rb["losses"]["base_loss"])) < 1e-6
 
 
 def test_shared_patch_embed_and_fused_task_id_equal_the_two_pass_form(engines):
