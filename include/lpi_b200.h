@@ -138,6 +138,18 @@ int lpi_attn_bwd(const void* qkv, const void* out, const void* d_out, const floa
 int lpi_attn_fwd_f16(const void* qkv, void* out, float* lse2, int B, int L, int H, int causal, void* stream);
 int lpi_attn_bwd_f16(const void* qkv, const void* out, const void* d_out, const float* lse2, float* delta_ws, void* dqkv, int B, int L,
                      int H, int causal, void* stream);
+/* Attention of a tower's LAST block for the one query row per sample that the head reads: ln_post(x[:, 0, :]) in
+ * VisionTransformer.forward (models/clip/model.py:254-257), x[arange(B), tokenized.argmax(-1)] in TextEncoder.forward
+ * (models/clip/prompt_learner.py:57-61).  rows int32 [B] = global row (b*L + position) of each sample's read row; keys / values of
+ * all L positions (up to the row's own position when causal), L <= 512.  f16: 0 = bf16 storage, 1 = fp16.
+ * fwd: out_rows [B, H*64] = softmax(q K^T / 8) V of those rows; optionally x_rows [B, H*64] = x[rows] (fp32 residual rows gathered
+ *      by the same launch; x and x_rows are given together or both NULL).
+ * bwd: dqkv [B*L, 3*H*64] is written completely (dq zero outside the read rows, dk / dv zero beyond the causal horizon), linear in
+ *      dout_rows [B, H*64]; optionally g[rows] = g_rows (fp32 [B, H*64] scattered into the caller-zeroed [B*L, H*64] stream). */
+int lpi_attn_rowq_fwd(const void* qkv, const int* rows, void* out_rows, const float* x, float* x_rows, int B, int L, int H, int causal,
+                      int f16, void* stream);
+int lpi_attn_rowq_bwd(const void* qkv, const int* rows, const void* dout_rows, void* dqkv, const float* g_rows, float* g, int B, int L,
+                      int H, int causal, int f16, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * LayerNorm in fp32 (models/clip/model.py:154-160; eps inside the sqrt, biased variance).

@@ -93,6 +93,7 @@ class TowerTape:
     L: int
     blocks: List[BlockSaved] = field(default_factory=list)
     x_final: Optional[torch.Tensor] = None
+    out_rows: Optional[torch.Tensor] = None      # int32 [B]: the last block ran on these rows only (Tower.forward, out_rows)
     injected: Dict[int, bool] = field(default_factory=dict)
 
 
@@ -119,20 +120,43 @@ class Tower:
         self.causal = causal
         self.width = heads * 64
         self.dev = dev
+        # The head reads ONE row per sample of the last block's output (model.py:254-257, prompt_learner.py:57-61), so the last block
+        # computes its attention for that query row only (keys / values of every position) and its out_proj / ln_2 / MLP on [B, D]
+        # instead of [B*L, D]; the rows that are skipped reach neither the features nor any gradient.  LPI_LAST_BLOCK_FULL=1 (or
+        # last_block_rows = False) runs the full block instead; the tf32 / fp32 study modes always do.
+        self.last_block_rows = os.environ.get("LPI_LAST_BLOCK_FULL") != "1" and not self.tf32
 
     # -------------------------------------------------------------------------------------------- forward
     def forward(self, x: torch.Tensor, B: int, L: int, tape: Optional[TowerTape] = None,
-                inject: Optional[dict] = None) -> torch.Tensor:
+                inject: Optional[dict] = None, out_rows: Optional[torch.Tensor] = None) -> torch.Tensor:
         """x fp32 [B*L, D] (consumed).  `inject` = {'layers': {l,...}, 'table': [T, Lp, P, D] fp32, 'sel': int32[B] or None, 'P': P}
-        adds table[sel[b], l] to rows 1..P before block l (opt-in deep-prompt injection, l >= 1)."""
+        adds table[sel[b], l] to rows 1..P before block l (opt-in deep-prompt injection, l >= 1).
+        out_rows int32 [B] (only honoured when self.last_block_rows): the caller reads just these rows of the output -> the result is
+        [B, D], row b = output row out_rows[b]."""
         H = self.heads
         if self.tf32:
             return self._forward_tf32(x, B, L, tape, inject)
+        if not self.last_block_rows:
+            out_rows = None
+        n_blocks = len(self.blocks)
         for li, w in enumerate(self.blocks):
             if inject is not None and li != 0 and li in inject["layers"]:
                 ops.inject_prompt_rows(x, inject["table"][:, li].contiguous(), inject["sel"], B, L, inject["P"], self.width)
             _, h = ops.layernorm_fwd(x, w.ln1_g, w.ln1_b, half_dtype=self.half)
             qkv = ops.gemm(h, w.w_in, ops.EPI_BIAS_BF16, bias=w.b_in)
+            if out_rows is not None and li == n_blocks - 1:
+                # last block, read rows only: one query row per (sample, head) against all keys / values, then row-wise ops on [B, D]
+                o, xr = ops.attn_rowq_fwd(qkv, out_rows, B, L, H, self.causal, x=x)
+                x1 = ops.gemm(o, w.w_out, ops.EPI_BIAS_RESID_F32, bias=w.b_out, resid=xr)
+                _, h2 = ops.layernorm_fwd(x1, w.ln2_g, w.ln2_b, half_dtype=self.half)
+                z = torch.empty(B, 4 * self.width, device=x.device, dtype=self.half) if tape is not None else None
+                a = ops.gemm(h2, w.w_fc, ops.EPI_BIAS_GELU_BF16, bias=w.b_fc, out2=z)
+                x2 = ops.gemm(a, w.w_proj, ops.EPI_BIAS_RESID_F32, bias=w.b_proj, resid=x1)
+                if tape is not None:
+                    tape.blocks.append(BlockSaved(x=x, x1=x1, qkv=qkv, o=None, lse=None, z=z))
+                    tape.out_rows = out_rows
+                x = x2
+                break
             o, lse = ops.attn_fwd(qkv, B, L, H, self.causal, want_lse=tape is not None)
             if tape is not None:
                 x1 = ops.gemm(o, w.w_out, ops.EPI_BIAS_RESID_F32, bias=w.b_out, resid=x)
@@ -204,7 +228,8 @@ class Tower:
                  inject_grads: Optional[dict] = None) -> torch.Tensor:
         """g fp32 [B*L, D] = d loss / d (tower output), updated in place down to d loss / d (tower input);
         g_bf16 is its 16-bit shadow (must match g on entry; bf16, or fp16 holding grad_scale * g for an fp16 tower).  With `inject`, inject_grads[l] receives
-        sum_b g_l[b, 1:P+1] for every injected layer."""
+        sum_b g_l[b, 1:P+1] for every injected layer.  When the forward ran its last block on the read rows (tape.out_rows), g and g_bf16
+        are [B, D] (gradient of those rows) and the [B*L, D] stream is allocated here: always use the RETURNED tensor."""
         B, L, H = tape.B, tape.L, self.heads
         if self.tf32:
             return self._backward_tf32(tape, g, inject, inject_grads)
@@ -214,7 +239,14 @@ class Tower:
             dh2 = ops.gemm(dz, w.w_fc_t, self.epi_dh)
             ops.layernorm_bwd(dh2, s.x1, w.ln2_g, g, g_bf16, accumulate=True, grad_scale=self.grad_scale)
             do = ops.gemm(g_bf16, w.w_out_t, ops.EPI_BF16)
-            dqkv = ops.attn_bwd(s.qkv, s.o, do, s.lse, B, L, H, self.causal)
+            if tape.out_rows is not None and li == len(self.blocks) - 1:
+                # the last block ran on the read rows: g / g_bf16 are [B, D] up to here; dk / dv of every position (and dq of the read
+                # rows) come from the one-row attention backward, which also drops the residual-path gradient into the full stream
+                gf = torch.zeros(B * L, self.width, device=g.device, dtype=torch.float32)
+                dqkv = ops.attn_rowq_bwd(s.qkv, tape.out_rows, do, B, L, H, self.causal, g_rows=g, g=gf)
+                g, g_bf16 = gf, torch.empty(B * L, self.width, device=g.device, dtype=self.half)
+            else:
+                dqkv = ops.attn_bwd(s.qkv, s.o, do, s.lse, B, L, H, self.causal)
             dh1 = ops.gemm(dqkv, w.w_in_t, self.epi_dh)
             ops.layernorm_bwd(dh1, s.x, w.ln1_g, g, g_bf16, accumulate=True, grad_scale=self.grad_scale)
             if inject is not None and li != 0 and li in inject["layers"] and inject_grads is not None:
@@ -292,8 +324,10 @@ class VisionEngine:
                 raise ValueError("deep-prompt injection (inject_layers) needs the reconstructed prompt_table as well as the factors")
             inject = {"layers": set(int(l) for l in inject_layers), "table": prompt_table, "sel": sel, "P": P}
         ttape = TowerTape(B, L) if tape is not None else None
-        x = self.tower.forward(x, B, L, ttape, inject)
-        rows = torch.arange(B, device=x.device, dtype=torch.int32) * L
+        rows = torch.arange(B, device=x.device, dtype=torch.int32) * L          # the CLS rows: all the head reads (model.py:254)
+        x = self.tower.forward(x, B, L, ttape, inject, out_rows=rows)
+        if self.tower.last_block_rows:
+            rows = torch.arange(B, device=x.device, dtype=torch.int32)          # x is [B, D] already
         task_id = None
         if centers is not None:
             feat, z, task_id = ops.head_fwd_select(x, rows, self.ln_post[0], self.ln_post[1], self.proj, centers)
@@ -321,12 +355,13 @@ class VisionEngine:
         normalised feature, dz = gradient wrt the raw projection (either may be None)."""
         B, L, D, P = tape["B"], tape["L"], self.width, tape["P"]
         dev = tape["x"].device
-        g = torch.zeros(B * L, D, device=dev, dtype=torch.float32)
-        gb = torch.zeros(B * L, D, device=dev, dtype=self.tower.half)
+        n_rows = tape["x"].shape[0]          # B when the last block ran on the read rows only, else B * L
+        g = torch.zeros(n_rows, D, device=dev, dtype=torch.float32)
+        gb = torch.zeros(n_rows, D, device=dev, dtype=self.tower.half)
         ops.head_bwd(None if dfeat is None else dfeat.contiguous(), None if dz is None else dz.contiguous(), tape["z"], tape["x"],
                      tape["rows"], self.ln_post[0], self.proj, g, gb, grad_scale=self.tower.grad_scale)
         inj_grads = {}
-        self.tower.backward(tape["tower"], g, gb, tape["inject"], inj_grads)
+        g = self.tower.backward(tape["tower"], g, gb, tape["inject"], inj_grads)
         if P == 0:
             return None
         G = torch.zeros(tape["n_tables"], tape["Lp"], P, D, device=dev, dtype=torch.float32)
@@ -391,8 +426,10 @@ class TextEngine:
                 raise ValueError("deep-prompt injection (inject_layers) needs the reconstructed prompt_table as well as the factors")
             inject = {"layers": set(int(l) for l in inject_layers), "table": prompt_table, "sel": sel, "P": P}
         ttape = TowerTape(B, L) if tape is not None else None
-        x = self.tower.forward(x, B, L, ttape, inject)
         rows = (torch.arange(B, device=x.device, dtype=torch.int64) * L + tokens.argmax(dim=-1)).to(torch.int32)   # EOT row
+        x = self.tower.forward(x, B, L, ttape, inject, out_rows=rows)
+        if self.tower.last_block_rows:
+            rows = torch.arange(B, device=x.device, dtype=torch.int32)          # x is [B, D] already
         feat, z = ops.head_fwd(x, rows, self.ln_final[0], self.ln_final[1], self.proj)
         if tape is not None:
             n_tables = 0 if P == 0 else (factors[0].shape[0] if factors is not None else prompt_table.shape[0])
@@ -403,12 +440,13 @@ class TextEngine:
     def backward(self, tape: dict, dfeat: Optional[torch.Tensor], dz: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
         B, L, D, P = tape["B"], tape["L"], self.width, tape["P"]
         dev = tape["x"].device
-        g = torch.zeros(B * L, D, device=dev, dtype=torch.float32)
-        gb = torch.zeros(B * L, D, device=dev, dtype=self.tower.half)
+        n_rows = tape["x"].shape[0]          # B when the last block ran on the read rows only, else B * L
+        g = torch.zeros(n_rows, D, device=dev, dtype=torch.float32)
+        gb = torch.zeros(n_rows, D, device=dev, dtype=self.tower.half)
         ops.head_bwd(None if dfeat is None else dfeat.contiguous(), None if dz is None else dz.contiguous(), tape["z"], tape["x"],
                      tape["rows"], self.ln_final[0], self.proj, g, gb, grad_scale=self.tower.grad_scale)
         inj_grads = {}
-        self.tower.backward(tape["tower"], g, gb, tape["inject"], inj_grads)
+        g = self.tower.backward(tape["tower"], g, gb, tape["inject"], inj_grads)
         if P == 0:
             return None
         G = torch.zeros(tape["n_tables"], tape["Lp"], P, D, device=dev, dtype=torch.float32)
@@ -427,8 +465,10 @@ class TextEngine:
         if prompt_table is not None and len(inject_layers) > 0:
             inject = {"layers": set(int(l) for l in inject_layers), "table": prompt_table, "sel": sel, "P": prompt_table.shape[2]}
         ttape = TowerTape(B, L) if tape is not None else None
-        x = self.tower.forward(x, B, L, ttape, inject)
         rows = (torch.arange(B, device=x.device, dtype=torch.int64) * L + tokens.argmax(dim=-1)).to(torch.int32)
+        x = self.tower.forward(x, B, L, ttape, inject, out_rows=rows)
+        if self.tower.last_block_rows:
+            rows = torch.arange(B, device=x.device, dtype=torch.int32)
         feat, z = ops.head_fwd(x, rows, self.ln_final[0], self.ln_final[1], self.proj)
         if tape is not None:
             tape.update(dict(tower=ttape, rows=rows, z=z, x=x, sel=sel, L=L, B=B, inject=inject,
@@ -439,12 +479,13 @@ class TextEngine:
         """-> (d loss / d prompts [B*L, D], d loss / d prompt_table or None)"""
         B, L, D = tape["B"], tape["L"], self.width
         dev = tape["x"].device
-        g = torch.zeros(B * L, D, device=dev, dtype=torch.float32)
-        gb = torch.zeros(B * L, D, device=dev, dtype=self.tower.half)
+        n_rows = tape["x"].shape[0]          # B when the last block ran on the read rows only, else B * L
+        g = torch.zeros(n_rows, D, device=dev, dtype=torch.float32)
+        gb = torch.zeros(n_rows, D, device=dev, dtype=self.tower.half)
         ops.head_bwd(None if dfeat is None else dfeat.contiguous(), None if dz is None else dz.contiguous(), tape["z"], tape["x"],
                      tape["rows"], self.ln_final[0], self.proj, g, gb, grad_scale=self.tower.grad_scale)
         inj_grads = {}
-        self.tower.backward(tape["tower"], g, gb, tape["inject"], inj_grads)
+        g = self.tower.backward(tape["tower"], g, gb, tape["inject"], inj_grads)
         G = None
         if tape["table_shape"] is not None:
             G = torch.zeros(tape["table_shape"], device=dev, dtype=torch.float32)

@@ -378,6 +378,46 @@ def attn_bwd(qkv, out, d_out, lse, B: int, L: int, H: int, causal: bool, dqkv: O
     return dqkv
 
 
+def attn_rowq_fwd(qkv: torch.Tensor, rows: torch.Tensor, B: int, L: int, H: int, causal: bool, x: Optional[torch.Tensor] = None):
+    """Attention of the one query row per sample the head reads (last block of a tower; model.py:254-257, prompt_learner.py:57-61).
+    qkv [B*L, 3*H*64] bf16 / fp16, rows int32 [B] (global row indices) -> out_rows [B, H*64]; with x (fp32 [B*L, H*64]) also x[rows]."""
+    _lib.require_device()
+    h = qkv.dtype
+    if h not in (torch.bfloat16, torch.float16):
+        raise _lib.LpiError(f"qkv must be bf16 or fp16, got {qkv.dtype}")
+    _chk(qkv, h, "qkv")
+    _chk(rows, torch.int32, "rows")
+    assert qkv.shape == (B * L, 3 * H * 64) and rows.shape == (B,)
+    out = torch.empty(B, H * 64, device=qkv.device, dtype=h)
+    x_rows = None
+    if x is not None:
+        _chk(x, torch.float32, "x")
+        assert x.shape == (B * L, H * 64)
+        x_rows = torch.empty(B, H * 64, device=qkv.device, dtype=torch.float32)
+    call("attn_rowq_fwd", ptr(qkv), ptr(rows), ptr(out), ptr(x), ptr(x_rows), B, L, H, int(causal), int(h == torch.float16), stream_ptr())
+    _count()
+    return out, x_rows
+
+
+def attn_rowq_bwd(qkv: torch.Tensor, rows: torch.Tensor, d_out_rows: torch.Tensor, B: int, L: int, H: int, causal: bool,
+                  g_rows: Optional[torch.Tensor] = None, g: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """-> dqkv [B*L, 3*H*64] (complete: zero where the read rows have no influence); with g_rows / g also g[rows] = g_rows."""
+    h = qkv.dtype
+    _chk(qkv, h, "qkv")
+    _chk(d_out_rows, h, "d_out_rows")
+    _chk(rows, torch.int32, "rows")
+    assert d_out_rows.shape == (B, H * 64)
+    if g is not None:
+        _chk(g, torch.float32, "g")
+        _chk(g_rows, torch.float32, "g_rows")
+        assert g.shape == (B * L, H * 64) and g_rows.shape == (B, H * 64)
+    dqkv = torch.empty_like(qkv)
+    call("attn_rowq_bwd", ptr(qkv), ptr(rows), ptr(d_out_rows), ptr(dqkv), ptr(g_rows), ptr(g), B, L, H, int(causal),
+         int(h == torch.float16), stream_ptr())
+    _count()
+    return dqkv
+
+
 # ------------------------------------------------------------------------------------------ LayerNorm / front ends / heads
 LN_EPS = 1e-5
 

@@ -377,3 +377,47 @@ def test_head_fwd_select_equals_head_plus_nearest_center():
     assert torch.equal(f, f2) and torch.equal(z, z2)
     want = ops.nearest_center_l1(f, keys.contiguous())
     assert torch.equal(sel.long(), want) and int(sel[11]) == 4
+
+
+@pytest.mark.parametrize("B,L,H,causal,dtype", [(3, 77, 8, True, torch.float16), (2, 213, 12, False, torch.float16),
+                                                (4, 39, 8, True, torch.bfloat16), (1, 1, 1, False, torch.bfloat16),
+                                                (2, 300, 2, True, torch.float16)])
+def test_attention_row_query_fwd_bwd(B, L, H, causal, dtype):
+    """lpi_attn_rowq_*: the last block's attention for the one row per sample the head reads (model.py:254-257,
+    prompt_learner.py:57-61) == the full attention at those rows; its backward == autograd of a loss that reads those rows only
+    (dq zero elsewhere, dk / dv complete); x[rows] gathered and g[rows] scattered by the same launches."""
+    g = torch.Generator().manual_seed(L * 13 + H)
+    D = H * 64
+    qkv = (torch.randn(B * L, 3 * D, generator=g) * 1.5).cuda().to(dtype)
+    pos = torch.randint(0, L, (B,), generator=g)
+    pos[0] = L - 1
+    rows = (torch.arange(B) * L + pos).to(torch.int32).cuda()
+    x = torch.randn(B * L, D, generator=g).cuda()
+    out_rows, x_rows = ops.attn_rowq_fwd(qkv, rows, B, L, H, causal, x=x)
+    assert torch.equal(x_rows, x[rows.long()])
+    qr = qkv.float().requires_grad_(True)
+    ref, _ = _ref_attention(qr, B, L, H, causal)
+    ref_rows = ref[rows.long()]
+    tol = 2e-3 if dtype == torch.float16 else 1e-2                    # fp32 arithmetic; only the output is rounded to 16 bits
+    assert out_rows.dtype == dtype and (out_rows.float() - ref_rows).abs().max() < tol * ref_rows.abs().max()
+    d_rows = torch.randn(B, D, generator=g).cuda().to(dtype)
+    ref_rows.backward(d_rows.float())
+    g_rows = torch.randn(B, D, generator=g).cuda()
+    gfull = torch.zeros(B * L, D, device="cuda")
+    dqkv = ops.attn_rowq_bwd(qkv, rows, d_rows, B, L, H, causal, g_rows=g_rows, g=gfull)
+    want_g = torch.zeros_like(gfull)
+    want_g[rows.long()] = g_rows
+    assert torch.equal(gfull, want_g)
+    assert dqkv.dtype == dtype and dqkv.shape == qkv.shape
+    gt = qr.grad
+    scale = gt.abs().max().clamp_min(1e-6)
+    assert (dqkv.float() - gt).abs().max() < (4e-3 if dtype == torch.float16 else 2e-2) * scale
+    dead = gt == 0
+    if dead.any():
+        assert dqkv.float()[dead].abs().max() == 0                     # exact zeros where the read rows have no influence
+    # linear in d_out: the fp16 gradient scale passes through
+    if dtype == torch.float16:
+        d_small = (d_rows.float() * 2 ** -10).half()
+        a = ops.attn_rowq_bwd(qkv, rows, d_small, B, L, H, causal)
+        b2 = ops.attn_rowq_bwd(qkv, rows, (d_small.float() * 1024).half(), B, L, H, causal)
+        assert _rel(b2.float(), a.float() * 1024) < 2e-3

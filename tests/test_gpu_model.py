@@ -239,3 +239,33 @@ def test_fp32_parity_mode_matches_reference_to_1e5(clip_sd, golden_model, golden
             assert abs(float(r["losses"][k]) - v) < 1e-5 * max(abs(v), 1e-3), (task, k, float(r["losses"][k]), v)
         for k in O.FACTOR_NAMES:
             assert _rel(r["grads"][k], want["grads"][k]) < 1e-4, (task, k, _rel(r["grads"][k], want["grads"][k]))
+
+
+def test_last_block_on_read_rows_equals_the_full_block(engines):
+    """The head reads one row per sample (CLS, model.py:254-257; EOT, prompt_learner.py:57-61), so the last block runs its attention
+    for that query row only and its out_proj / ln_2 / MLP on [B, D] (Tower.last_block_rows).  Features, projections and the prompt
+    gradients must be those of the full block (same maths; the one-row attention is fp32 arithmetic where the full kernel rounds P to
+    16 bits, hence tolerances instead of equality), for both towers, with and without deep injection."""
+    vision, text = engines
+    B = 5
+    images, tokens = S.make_images(B, 31).cuda(), S.make_tokens(B, 31).cuda()
+    fac = {k: v.cuda() for k, v in S.make_prompt_factors(6).items()}
+    vis, txt = lpi_step.reconstruct(fac)
+    d = torch.randn(B, 512, generator=torch.Generator().manual_seed(3)).cuda() * 1e-2
+    for eng, inp, table in ((vision, images, vis), (text, tokens, txt)):
+        for inject in ((), (1, 8)):
+            res = []
+            for rows_only in (False, True):
+                eng.tower.last_block_rows = rows_only
+                try:
+                    tape = {}
+                    f, z = eng.forward(inp, table.unsqueeze(0), None, tape, inject)
+                    G = eng.backward(tape, d, d * 0.5)
+                    f_eval, _ = eng.forward(inp, table.unsqueeze(0), None, None, inject)          # the in-place (no tape) form
+                finally:
+                    eng.tower.last_block_rows = True
+                assert tape["x"].shape[0] == (B if rows_only else B * tape["L"])
+                res.append((f, z, G, f_eval))
+            (f0, z0, G0, e0), (f1, z1, G1, e1) = res
+            assert _rel(f1, f0) < 1e-3 and _rel(z1, z0) < 1e-3 and _rel(e1, f1) < 1e-6 and _rel(e0, f0) < 1e-6
+            assert _rel(G1, G0) < 5e-3, (type(eng).__name__, inject, _rel(G1, G0))
