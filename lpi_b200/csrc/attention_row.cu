@@ -119,6 +119,7 @@ __global__ void __launch_bounds__(ROW_THREADS)
 attn_rowq_fwd_kernel(const T* __restrict__ qkv, const int* __restrict__ rows, T* __restrict__ out_rows, const float* __restrict__ x,
                      float* __restrict__ x_rows, int B, int L, int H, int causal) {
     __shared__ float sQ[HD], sO[HD], sP[MAX_L], part[(ROW_THREADS / 32) * HD], red[ROW_THREADS / 32];
+    pdl_enter();
     const int h = blockIdx.x, b = blockIdx.y;
     const int D = H * HD;
     const size_t ld = size_t(3) * D;
@@ -145,6 +146,7 @@ __global__ void __launch_bounds__(ROW_THREADS)
 attn_rowq_bwd_kernel(const T* __restrict__ qkv, const int* __restrict__ rows, const T* __restrict__ dout_rows, T* __restrict__ dqkv,
                      const float* __restrict__ g_rows, float* __restrict__ g, int B, int L, int H, int causal) {
     __shared__ float sQ[HD], sDO[HD], sDQ[HD], sP[MAX_L], sDS[MAX_L], part[(ROW_THREADS / 32) * HD], red[ROW_THREADS / 32];
+    pdl_enter();
     const int h = blockIdx.x, b = blockIdx.y;
     const int D = H * HD;
     const size_t ld = size_t(3) * D;
@@ -191,15 +193,15 @@ attn_rowq_bwd_kernel(const T* __restrict__ qkv, const int* __restrict__ rows, co
 
 template <typename T>
 int rowq_fwd(const void* qkv, const int* rows, void* out_rows, const float* x, float* x_rows, int B, int L, int H, int causal, cudaStream_t st) {
-    attn_rowq_fwd_kernel<T><<<dim3(H, B), ROW_THREADS, 0, st>>>(static_cast<const T*>(qkv), rows, static_cast<T*>(out_rows), x, x_rows, B, L, H, causal);
+    launch_pdl(attn_rowq_fwd_kernel<T>, dim3(H, B), dim3(ROW_THREADS), 0, st, static_cast<const T*>(qkv), rows, static_cast<T*>(out_rows), x, x_rows, B, L, H, causal);
     return check_launch("attn_rowq_fwd");
 }
 
 template <typename T>
 int rowq_bwd(const void* qkv, const int* rows, const void* dout_rows, void* dqkv, const float* g_rows, float* g, int B, int L, int H,
              int causal, cudaStream_t st) {
-    attn_rowq_bwd_kernel<T><<<dim3(H, B), ROW_THREADS, 0, st>>>(static_cast<const T*>(qkv), rows, static_cast<const T*>(dout_rows),
-                                                               static_cast<T*>(dqkv), g_rows, g, B, L, H, causal);
+    launch_pdl(attn_rowq_bwd_kernel<T>, dim3(H, B), dim3(ROW_THREADS), 0, st, static_cast<const T*>(qkv), rows, static_cast<const T*>(dout_rows),
+               static_cast<T*>(dqkv), g_rows, g, B, L, H, causal);
     return check_launch("attn_rowq_bwd");
 }
 

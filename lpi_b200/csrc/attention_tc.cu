@@ -130,6 +130,8 @@ attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    pdl_launch_dependents();
+    pdl_wait();                                            // barriers / TMEM above overlap the previous kernel's tail (PDL)
 
     if (warp == 4) {
         if (lane == 0) {
@@ -398,6 +400,13 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
                 mbar_init(bar_out(u), 1);
             }
             fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc<512>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
+        if (lane == 0) {
+            // PDL: everything above overlaps the tail of the previous kernel; its outputs (qkv, dO) are read from here on
+            pdl_launch_dependents();
+            pdl_wait();
             const uint32_t bytes = uint32_t(p.rows) * 128u;
             mbar_arrive_expect_tx(bar_ld0, 2 * bytes);
             tma_load_3d(sQ, &tmQKV, bar_ld0, h * 64, 0, b);
@@ -406,13 +415,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
             tma_load_3d(sdO, &tmDO, bar_ld1, h * 64, 0, b);
             tma_load_3d(sV, &tmQKV, bar_ld1, 2 * D + h * 64, 0, b);
         }
-        __syncwarp();
-        tmem_alloc<512>(smem_u32(const_cast<uint32_t*>(tmem_slot)));
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    pdl_wait();                                            // every thread, before its first global-memory access (lse / delta / outputs)
 
     if (warp == CTRL_WARP) {
         if (lane == 0) {
@@ -670,11 +678,11 @@ int attn_fwd_tc(const void* qkv, void* out, float* out_f32, float* lse2, int B, 
         configured = true;
     }
     if (causal) {
-        if (f16) attn_fwd_tc_kernel<true, true><<<grid, FWD_THREADS, FWD_SMEM, st>>>(tmQ, tmKV, a);
-        else attn_fwd_tc_kernel<true, false><<<grid, FWD_THREADS, FWD_SMEM, st>>>(tmQ, tmKV, a);
+        if (f16) launch_pdl(attn_fwd_tc_kernel<true, true>, grid, dim3(FWD_THREADS), FWD_SMEM, st, tmQ, tmKV, a);
+        else launch_pdl(attn_fwd_tc_kernel<true, false>, grid, dim3(FWD_THREADS), FWD_SMEM, st, tmQ, tmKV, a);
     } else {
-        if (f16) attn_fwd_tc_kernel<false, true><<<grid, FWD_THREADS, FWD_SMEM, st>>>(tmQ, tmKV, a);
-        else attn_fwd_tc_kernel<false, false><<<grid, FWD_THREADS, FWD_SMEM, st>>>(tmQ, tmKV, a);
+        if (f16) launch_pdl(attn_fwd_tc_kernel<false, true>, grid, dim3(FWD_THREADS), FWD_SMEM, st, tmQ, tmKV, a);
+        else launch_pdl(attn_fwd_tc_kernel<false, false>, grid, dim3(FWD_THREADS), FWD_SMEM, st, tmQ, tmKV, a);
     }
     return check_launch("attn_fwd_tc");
 }
@@ -706,13 +714,13 @@ int attn_bwd_tc(const void* qkv, const void* d_out, const float* lse2, const flo
     }
     const bool f32 = dqkv_f32 != nullptr;
     if (causal) {
-        if (f16) attn_bwd_tc_kernel<true, false, true><<<grid, BWD_THREADS, BWD_SMEM, st>>>(tmQKV, tmDO, tmOut, a);
-        else if (f32) attn_bwd_tc_kernel<true, true, false><<<grid, BWD_THREADS, BWD_SMEM, st>>>(tmQKV, tmDO, tmOut, a);
-        else attn_bwd_tc_kernel<true, false, false><<<grid, BWD_THREADS, BWD_SMEM, st>>>(tmQKV, tmDO, tmOut, a);
+        if (f16) launch_pdl(attn_bwd_tc_kernel<true, false, true>, grid, dim3(BWD_THREADS), BWD_SMEM, st, tmQKV, tmDO, tmOut, a);
+        else if (f32) launch_pdl(attn_bwd_tc_kernel<true, true, false>, grid, dim3(BWD_THREADS), BWD_SMEM, st, tmQKV, tmDO, tmOut, a);
+        else launch_pdl(attn_bwd_tc_kernel<true, false, false>, grid, dim3(BWD_THREADS), BWD_SMEM, st, tmQKV, tmDO, tmOut, a);
     } else {
-        if (f16) attn_bwd_tc_kernel<false, false, true><<<grid, BWD_THREADS, BWD_SMEM, st>>>(tmQKV, tmDO, tmOut, a);
-        else if (f32) attn_bwd_tc_kernel<false, true, false><<<grid, BWD_THREADS, BWD_SMEM, st>>>(tmQKV, tmDO, tmOut, a);
-        else attn_bwd_tc_kernel<false, false, false><<<grid, BWD_THREADS, BWD_SMEM, st>>>(tmQKV, tmDO, tmOut, a);
+        if (f16) launch_pdl(attn_bwd_tc_kernel<false, false, true>, grid, dim3(BWD_THREADS), BWD_SMEM, st, tmQKV, tmDO, tmOut, a);
+        else if (f32) launch_pdl(attn_bwd_tc_kernel<false, true, false>, grid, dim3(BWD_THREADS), BWD_SMEM, st, tmQKV, tmDO, tmOut, a);
+        else launch_pdl(attn_bwd_tc_kernel<false, false, false>, grid, dim3(BWD_THREADS), BWD_SMEM, st, tmQKV, tmDO, tmOut, a);
     }
     return check_launch("attn_bwd_tc");
 }

@@ -1,6 +1,7 @@
 // Error reporting and device checks for liblpi_b200.so.
 #include "lpi_internal.h"
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace lpi {
@@ -19,6 +20,15 @@ int check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_error(LPI_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
     return LPI_OK;
+}
+
+bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("LPI_PDL");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on == 1;
 }
 
 }  // namespace lpi

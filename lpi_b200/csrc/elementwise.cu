@@ -62,6 +62,7 @@ __device__ __forceinline__ void ln_apply_store(const float4 (&v)[NV], RowStats s
 template <int NV, bool F16 = false>
 __global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                                      float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_bf16, long M, int D, float eps) {
+    pdl_enter();
     const long row = (long(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     if (row >= M) return;
     const int lane = threadIdx.x & 31;
@@ -109,6 +110,7 @@ template <int NV, bool F16 = false, bool DY16 = false>
 __global__ void layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
                                      float* __restrict__ g, __nv_bfloat16* __restrict__ g_bf16, long M, int D, float eps, int accumulate,
                                      float dy_scale = 1.0f, float shadow_scale = 1.0f) {
+    pdl_enter();
     const long row = (long(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     if (row >= M) return;
     const int lane = threadIdx.x & 31;
@@ -521,8 +523,8 @@ extern "C" int lpi_layernorm_fwd(const float* x, const float* gamma, const float
     if (!out_f32 && !out_bf16) return set_error(LPI_ERR_ARG, "layernorm_fwd: no output");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int rc = dispatch_nv(D, [&](auto nv) {
-        layernorm_fwd_kernel<decltype(nv)::value><<<warp_grid(M, 256), 256, 0, st>>>(x, gamma, beta, out_f32,
-                                                                                       static_cast<__nv_bfloat16*>(out_bf16), M, D, eps);
+        launch_pdl(layernorm_fwd_kernel<decltype(nv)::value>, dim3(warp_grid(M, 256)), dim3(256), 0, st, x, gamma, beta, out_f32,
+                   static_cast<__nv_bfloat16*>(out_bf16), long(M), D, eps);
         return 0;
     });
     return rc ? rc : check_launch("layernorm_fwd");
@@ -534,8 +536,8 @@ extern "C" int lpi_layernorm_fwd_f16(const float* x, const float* gamma, const f
     if (!out_f32 && !out_f16) return set_error(LPI_ERR_ARG, "layernorm_fwd_f16: no output");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int rc = dispatch_nv(D, [&](auto nv) {
-        layernorm_fwd_kernel<decltype(nv)::value, true><<<warp_grid(M, 256), 256, 0, st>>>(x, gamma, beta, out_f32,
-                                                                                          static_cast<__nv_bfloat16*>(out_f16), M, D, eps);
+        launch_pdl(layernorm_fwd_kernel<decltype(nv)::value, true>, dim3(warp_grid(M, 256)), dim3(256), 0, st, x, gamma, beta, out_f32,
+                   static_cast<__nv_bfloat16*>(out_f16), long(M), D, eps);
         return 0;
     });
     return rc ? rc : check_launch("layernorm_fwd_f16");
@@ -547,8 +549,8 @@ extern "C" int lpi_layernorm_bwd_f16(const float* dy_scaled, const float* x, con
     if (!(grad_scale > 0.f)) return set_error(LPI_ERR_ARG, "layernorm_bwd_f16: grad_scale must be positive");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int rc = dispatch_nv(D, [&](auto nv) {
-        layernorm_bwd_kernel<decltype(nv)::value, true><<<warp_grid(M, 128), 128, 0, st>>>(dy_scaled, x, gamma, g, static_cast<__nv_bfloat16*>(g_f16),
-                                                                                          M, D, eps, accumulate, 1.0f / grad_scale, grad_scale);
+        launch_pdl(layernorm_bwd_kernel<decltype(nv)::value, true>, dim3(warp_grid(M, 128)), dim3(128), 0, st, dy_scaled, x, gamma, g,
+                   static_cast<__nv_bfloat16*>(g_f16), long(M), D, eps, accumulate, 1.0f / grad_scale, grad_scale);
         return 0;
     });
     return rc ? rc : check_launch("layernorm_bwd_f16");
@@ -563,8 +565,8 @@ extern "C" int lpi_layernorm_bwd_dy16(const void* dy16, int is_f16, const float*
     auto gh = static_cast<__nv_bfloat16*>(g16);
     const int rc = dispatch_nv(D, [&](auto nv) {
         constexpr int NV = decltype(nv)::value;
-        if (is_f16) layernorm_bwd_kernel<NV, true, true><<<warp_grid(M, 128), 128, 0, st>>>(dy, x, gamma, g, gh, M, D, eps, accumulate, 1.0f / grad_scale, grad_scale);
-        else layernorm_bwd_kernel<NV, false, true><<<warp_grid(M, 128), 128, 0, st>>>(dy, x, gamma, g, gh, M, D, eps, accumulate);
+        if (is_f16) launch_pdl(layernorm_bwd_kernel<NV, true, true>, dim3(warp_grid(M, 128)), dim3(128), 0, st, dy, x, gamma, g, gh, long(M), D, eps, accumulate, 1.0f / grad_scale, grad_scale);
+        else launch_pdl(layernorm_bwd_kernel<NV, false, true>, dim3(warp_grid(M, 128)), dim3(128), 0, st, dy, x, gamma, g, gh, long(M), D, eps, accumulate, 1.0f, 1.0f);
         return 0;
     });
     return rc ? rc : check_launch("layernorm_bwd_dy16");
@@ -575,8 +577,8 @@ extern "C" int lpi_layernorm_bwd(const float* dy, const float* x, const float* g
     if (M <= 0) return LPI_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int rc = dispatch_nv(D, [&](auto nv) {
-        layernorm_bwd_kernel<decltype(nv)::value><<<warp_grid(M, 128), 128, 0, st>>>(dy, x, gamma, g, static_cast<__nv_bfloat16*>(g_bf16), M,
-                                                                                       D, eps, accumulate);
+        launch_pdl(layernorm_bwd_kernel<decltype(nv)::value>, dim3(warp_grid(M, 128)), dim3(128), 0, st, dy, x, gamma, g,
+                   static_cast<__nv_bfloat16*>(g_bf16), long(M), D, eps, accumulate, 1.0f, 1.0f);
         return 0;
     });
     return rc ? rc : check_launch("layernorm_bwd");

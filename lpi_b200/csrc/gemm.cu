@@ -911,6 +911,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     cluster_sync_all();                          // peer barriers initialised before any remote arrive / multicast commit
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (MODE == MODE_GEMM) {
+        // PDL (lpi::launch_pdl): the set-up above ran while the previous kernel of the stream was finishing; its outputs (A, resid, aux)
+        // are touched only after this point.  The dependents of THIS kernel may be scheduled as its CTAs retire.
+        pdl_launch_dependents();
+        pdl_wait();
+    }
 
     // ---- work decomposition: a pure function of (cluster_id, rank), re-derived by every role
     // GEMM : cluster tile t -> (nt = t % num_n, mp = t / num_n), N fastest: the clusters running at the same time cover all N tiles of
@@ -1261,13 +1267,15 @@ static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     cfg.blockDim = dim3(PairCfg<MODE, BN>::THREADS);
     cfg.dynamicSmemBytes = PairCfg<MODE, BN>::SMEM_BYTES;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CL;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;      // see lpi_internal.h (launch_pdl) and the kernel's pdl_wait()
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = (MODE == MODE_GEMM && pdl_enabled()) ? 2 : 1;
     if (CL > 2) {
         // the kernel is persistent (one CTA per SM): a grid larger than what can be co-resident would run in two rounds.  4-CTA clusters
         // must sit inside one GPC, so fewer than sms / 4 of them may fit (GPCs with a TPC count that is not a multiple of two)

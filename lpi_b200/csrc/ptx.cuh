@@ -24,6 +24,19 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
+// Programmatic dependent launch (PDL).  A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization (lpi::launch_pdl) may
+// be scheduled while its predecessor in the stream is still running; everything before pdl_wait() (barrier init, TMEM allocation,
+// descriptor prefetch -- nothing that touches global memory) then overlaps the predecessor's tail, and pdl_wait() returns once the
+// predecessor grid has completed and its memory is visible.  pdl_launch_dependents() is the predecessor's side: "my dependents may be
+// scheduled".  Both are no-ops in a kernel launched without the attribute.  Rule kept by every kernel that uses them: every thread
+// executes pdl_wait() before its first global-memory access and before any early return.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// the usual prologue of a PDL kernel without set-up work of its own
+__device__ __forceinline__ void pdl_enter() {
+    pdl_launch_dependents();
+    pdl_wait();
+}
 __device__ __forceinline__ void fence_barrier_init() {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
@@ -260,6 +273,9 @@ __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
     return v;
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int threads) {      // producer side of bar.sync: does not block
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
