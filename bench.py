@@ -528,15 +528,22 @@ def sweep_leg(dev, args):
 
 
 # ------------------------------------------------------------------------------------------ train leg
-def train_flops_per_pair(text_len: int = 77):
+def train_flops_per_pair(text_len: int = 77, last_block_rows: bool = True):
     """(algorithmic, executed) GFLOP per image-text pair of one training step: 2 x linear + 3 x attention (fwd + dgrad, no wgrad) + the
-    patch embedding forward; `executed` counts the text positions the tower actually runs on."""
-    def tower(width, L):
-        return 24.0 * width * width * L * 12, 4.0 * L * L * width * 12
-    v_lin, v_att = tower(768, 213)
+    patch embedding forward.  `algorithmic` is the reference's own work (77 text positions, every row of every
+    block); `executed` counts what the towers actually run: the text positions up to the batch's last EOT, and in the LAST block of each
+    tower only the one row per sample the head reads for everything after the qkv projection (engine.Tower.last_block_rows: per
+    tower 18 w^2 (L - 1) linear and 4 w L (L - 1) attention FLOP less per pass)."""
+    def tower(width, L, trimmed_last):
+        lin, att = 24.0 * width * width * L * 12, 4.0 * L * L * width * 12
+        if trimmed_last:
+            lin -= 18.0 * width * width * (L - 1)
+            att -= 4.0 * width * L * (L - 1)
+        return lin, att
     out = []
-    for lt in (77, text_len):
-        t_lin, t_att = tower(512, lt)
+    for lt, trimmed in ((77, False), (text_len, last_block_rows)):
+        v_lin, v_att = tower(768, 213, trimmed)
+        t_lin, t_att = tower(512, lt, trimmed)
         out.append((2 * (v_lin + t_lin) + 3 * (v_att + t_att) + 2.0 * 196 * 768 * 768) / 1e9)
     return out[0], out[1]
 
@@ -697,7 +704,7 @@ def train_leg(dev, world, rank, group, steps, warmup, peaks, args, batch_per_gpu
 
     _, e2e_wall, _ = timed(e2e_step, steps)
     gb = batch_per_gpu * world
-    g_alg, g_exe = train_flops_per_pair(text_len)
+    g_alg, g_exe = train_flops_per_pair(text_len, vision.tower.last_block_rows)
     out = {"metric": "prompted_clip_train_pairs_per_sec", "value": gb / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms,
            "global_batch": gb, "parallelism": f"dp{world}", "launch_mode": mode, "launches_per_step": launches_per_step,
            "algorithmic_tflops": gb * g_alg / (ms * 1e-3) / 1e3, "executed_tflops": gb * g_exe / (ms * 1e-3) / 1e3,
@@ -705,6 +712,9 @@ def train_leg(dev, world, rank, group, steps, warmup, peaks, args, batch_per_gpu
            "precision": f"vision {vision.precision} / text fp16 operands, fp32 accumulate, fp32 residual stream / LayerNorm / heads / losses",
            "text_positions_executed": text_len, "text_positions_note": "77-token captions; the text tower runs on the positions up to the batch's last "
            "EOT (output-exact under the causal mask); algorithmic figures count the reference's full 77, executed figures the positions run",
+           "last_block_rows": bool(vision.tower.last_block_rows), "last_block_note": "the last block of each tower computes its attention / out_proj / "
+           "MLP only for the row the head reads (CLS, EOT): the other rows of that block reach neither the features nor any gradient; "
+           "algorithmic figures count the reference's full block, executed figures what runs",
            "workload": "BASELINE.json configs[2]: ViT-B/16 + 12-layer text, "
            "224x224 synthetic images, 77-token captions, random init, fwd + 3 losses + dgrad to 5 284 prompt scalars + SGD",
            "e2e": {"value": gb / (e2e_wall * 1e-3), "unit": "pairs/s", "ms_per_step": e2e_wall,

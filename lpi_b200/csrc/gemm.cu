@@ -63,6 +63,7 @@ struct GemmArgs {
     const float* aux_f32;          // [M, ldo] fp32 pre-activation (EPI_DGELU_F32)
     int ldo;
     int probe;                     // only in -DLPI_DEBUG_PROBE builds (tools/gemm_probe.py): 1 = the pair GEMM skips its A-tile loads (WRONG results, timing study)
+    int clc;                       // pair GEMM: 1 = one cluster per tile in the grid, resident clusters steal the pending ones (cluster launch control)
     int precise_act;               // fp16 outputs: 1 = ex2 + rcp sigmoid (2 MUFU ops), 0 = tanh.approx (1 MUFU op, |err| <= 2^-12)
     // MODE_TOPK
     int k;                         // top-k (<= TOPK_MAX)
@@ -839,6 +840,7 @@ struct PairCfg {
     // the GELU / dGELU / residual epilogues of the K = 768 GEMMs took ~2x their 48-MMA main loop (95 us for a 46 us GEMM)
     static constexpr int EPI_WARPS = (MODE == MODE_GEMM) ? 8 : 4;
     static constexpr int THREADS = 64 + 32 * EPI_WARPS;
+    static constexpr int CLC_SLOTS = 3;                      // response ring of the dynamic (cluster-launch-control) tile scheduler
     static constexpr int TAIL = (MODE == MODE_GEMM) ? EPI_WARPS * 32 * 32 * 4 : BM * TOPK_MAX * 8;
     static constexpr int SMEM_BYTES = LIST_OFF + TAIL + 1024;
     static constexpr int TMEM_COLS = 512;
@@ -873,6 +875,14 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const uint32_t afull_bar = bar_base + 8u * (2 * C::STAGES + 4);       // MODE_TOPK: resident query tile landed / may be overwritten
     const uint32_t aempty_bar = bar_base + 8u * (2 * C::STAGES + 5);
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + C::BAR_OFF + 8 * (2 * C::STAGES + 6));
+    // dynamic tile scheduling (p.clc, MODE_GEMM with CTA pairs): a ring of CLC_SLOTS responses, each with a full barrier in every CTA
+    // (16 response bytes) and an empty barrier that lives in the leader CTA (all 19 consumers of the cluster arrive on it)
+    auto clc_full = [&](int s) { return bar_base + 8u * (2 * C::STAGES + 7 + s); };
+    auto clc_empty = [&](int s) { return bar_base + 8u * (2 * C::STAGES + 7 + C::CLC_SLOTS + s); };
+    auto clc_resp = [&](int s) { return bar_base + 208u + 16u * s; };
+    static_assert(8 * (2 * C::STAGES + 7 + 2 * C::CLC_SLOTS) <= 208 && 208 + 16 * C::CLC_SLOTS <= 256, "barrier region is 256 bytes");
+    constexpr int CLC_CONSUMERS = 2 * (1 + C::EPI_WARPS) + 1;     // TMA thread + epilogue warps of both CTAs, the leader's MMA thread
+    const bool clc = (MODE == MODE_GEMM) && (CL == 2) && p.clc != 0;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -901,6 +911,12 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             mbar_init(afull_bar, 1);
             mbar_init(aempty_bar, 1);
+            if (MODE == MODE_GEMM) {
+                for (int s2 = 0; s2 < C::CLC_SLOTS; ++s2) {
+                    mbar_init(clc_full(s2), 1);                 // the scheduler's arrive.expect_tx (16 response bytes)
+                    mbar_init(clc_empty(s2), CLC_CONSUMERS);
+                }
+            }
             fence_barrier_init();
         }
         __syncwarp();
@@ -931,13 +947,42 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // chunk-fastest order, which lets the chunks of one query tile warm each other up from the first wave on, measured 7 % SLOWER
     // (625 k rows: 12.10 vs 11.34 ms; the exact-threshold run slows down as well, i.e. it is the lost L2 locality of the gallery stream)
     constexpr bool topk_qmajor = false;
+    // Tile sequence of this cluster.  Static mode: t = cluster_id, + n_clusters, ...  Dynamic mode (clc): the grid holds one cluster per
+    // tile; a cluster starts with its own tile and then takes over the tiles of clusters that have not been launched yet, in launch
+    // order, until none is left -- late starters (SMs still busy with the previous kernel or with the other tower's stream) simply
+    // take fewer tiles instead of holding the whole kernel back.  Every role walks the same response ring.
+    const uint32_t clc_empty_leader_base = mapa_u32(clc_empty(0), 0);
+    auto next_tile = [&](int t, int& slot, uint32_t& ph, bool release) -> int {
+        if (!clc) return t + n_clusters;
+        mbar_wait(clc_full(slot), ph);
+        const int x = clc_decode(clc_resp(slot));
+        fence_proxy_async_smem();                    // this read is ordered before the asynchronous rewrite of the slot
+        if (release) mbar_arrive_cluster(clc_empty_leader_base + 8u * slot);
+        if (++slot == C::CLC_SLOTS) { slot = 0; ph ^= 1; }
+        return x < 0 ? total : x / CL;
+    };
 
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer (one thread per CTA)
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0, aphase = 0;
-            for (int t = cluster_id; t < total; t += n_clusters) {
+            int cslot = 0, qslot = 0;
+            uint32_t cph = 0, qph = 0;
+            const uint32_t clc_full_peer = mapa_u32(clc_full(0), 1);
+            // dynamic mode: the leader's TMA thread is the tile scheduler.  ONE cancellation request per tile, issued when the last ring
+            // of k-blocks of the current tile is about to be requested: late enough that a cluster never hoards tiles it will only reach
+            // much later (with 2.9 tiles per cluster, three requests in flight per cluster cost up to one tile time of imbalance), early
+            // enough that the response (a round trip to the work distributor) is back when the loads of this tile have been issued.
+            auto clc_request = [&]() {
+                mbar_wait(clc_empty(qslot), qph ^ 1);           // every consumer of the cluster has read the slot's previous response
+                mbar_arrive_expect_tx(clc_full(qslot), 16);
+                mbar_arrive_expect_tx_cluster(clc_full_peer + 8u * qslot, 16);
+                clc_try_cancel_multicast(clc_resp(qslot), clc_full(qslot));
+                if (++qslot == C::CLC_SLOTS) { qslot = 0; qph ^= 1; }
+            };
+            const int kb_request = num_k > C::STAGES ? num_k - C::STAGES : 0;
+            for (int t = cluster_id; t < total; t = next_tile(t, cslot, cph, true)) {
                 const int mp = (MODE == MODE_GEMM) ? (CL == 4 ? NPAIR * (t / num_n) + int(pair) : (LPI_RASTER_N ? t / num_n : t % num_mp)) : (topk_qmajor ? t / p.n_chunks : t % num_mp);
                 const int second = (MODE == MODE_GEMM) ? ((CL == 4 || LPI_RASTER_N) ? t % num_n : t / num_mp) : (topk_qmajor ? t % p.n_chunks : t / num_mp);
                 const int m0 = (2 * mp + int(rank)) * BM;
@@ -955,6 +1000,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 for (int nt = n_begin; nt < n_end; ++nt) {
                     const int n0 = nt * BN + int(rank) * (BN / 2);  // this CTA streams its half of the B tile
                     for (int kb = 0; kb < num_k; ++kb) {
+                        if (MODE == MODE_GEMM && clc && leader && kb == kb_request) clc_request();
                         mbar_wait(empty_bar(stage), phase ^ 1);
 #ifdef LPI_DEBUG_PROBE
                         const bool skip_a = (MODE == MODE_GEMM) && p.probe == 1;
@@ -987,7 +1033,9 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             constexpr uint32_t idesc = make_idesc(TF32 ? kFmtTF32 : (F16 ? kFmtF16 : kFmtBF16), 2 * BM, BN, 0, 0);
             int stage = 0, acc = 0;
             uint32_t phase = 0, acc_phase = 0, aphase = 0;
-            for (int t = cluster_id; t < total; t += n_clusters) {
+            int cslot = 0;
+            uint32_t cph = 0;
+            for (int t = cluster_id; t < total; t = next_tile(t, cslot, cph, true)) {
                 const int second = (MODE == MODE_GEMM) ? ((CL == 4 || LPI_RASTER_N) ? t % num_n : t / num_mp) : (topk_qmajor ? t % p.n_chunks : t / num_mp);
                 int n_begin, n_end;
                 if (MODE == MODE_GEMM) { n_begin = second; n_end = second + 1; }
@@ -1033,7 +1081,17 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         TopkState tk{reinterpret_cast<float*>(smem_gen + C::LIST_OFF), reinterpret_cast<int*>(smem_gen + C::LIST_OFF + BM * TOPK_MAX * 4),
                      r_local, p.k, 0, -INFINITY};
         const uint32_t tempty_leader0 = mapa_u32(tempty_bar(0), 2 * pair), tempty_leader1 = mapa_u32(tempty_bar(1), 2 * pair);
-        for (int t = cluster_id; t < total; t += n_clusters) {
+        int cslot = 0;
+        uint32_t cph = 0;
+        // dynamic mode: every lane reads the response, lane 0 releases the slot once the whole warp has
+        auto next_tile_warp = [&](int t) -> int {
+            if (!clc) return t + n_clusters;
+            const int nt = next_tile(t, cslot, cph, false);
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(clc_empty_leader_base + 8u * ((cslot + C::CLC_SLOTS - 1) % C::CLC_SLOTS));
+            return nt;
+        };
+        for (int t = cluster_id; t < total; t = next_tile_warp(t)) {
             const int mp = (MODE == MODE_GEMM) ? (CL == 4 ? NPAIR * (t / num_n) + int(pair) : (LPI_RASTER_N ? t / num_n : t % num_mp)) : (topk_qmajor ? t / p.n_chunks : t % num_mp);
                 const int second = (MODE == MODE_GEMM) ? ((CL == 4 || LPI_RASTER_N) ? t % num_n : t / num_mp) : (topk_qmajor ? t % p.n_chunks : t / num_mp);
             const int m0 = (2 * mp + int(rank)) * BM;
@@ -1454,7 +1512,21 @@ static int gemm_entry(int op, const void* A, const void* B, int M, int N, int K,
     if (pair) {
         const long ctiles = (cl == 4 ? (mp_all + 1) / 2 : mp_all) * (N / pair_bn);
         const long max_cl = sms / cl;
-        const int n_clusters = int(ctiles < max_cl ? ctiles : max_cl);
+        // dynamic tile scheduling (cluster launch control): the grid holds one cluster per tile and the resident clusters take over the
+        // tiles of the pending ones.  Static round-robin over min(tiles, 74) persistent clusters with LPI_GEMM_CLC=0 (and for 4-CTA
+        // clusters / TF32 operands).
+        // OPT-IN (LPI_GEMM_CLC=1): per GEMM it is as fast as the static schedule once a cluster keeps only ONE request in flight, issued
+        // late in its tile (three in flight per cluster let clusters hoard tiles: +2-4 us on the 2.9-tiles-per-cluster shapes), but the
+        // training step gains nothing from it (8.37 vs 8.35 ms; vision tower alone 7.32 vs 7.38 ms), so the static schedule stays.
+        // (Capping the text tower's GEMMs to 8-37 persistent pairs so that they hold fewer SMs beside the vision tower was also measured:
+        // 8.50-8.95 ms against 8.48 ms without a cap.)
+        static int use_clc = -1;
+        if (use_clc < 0) {
+            const char* e = getenv("LPI_GEMM_CLC");
+            use_clc = (e && e[0] == '1') ? 1 : 0;
+        }
+        a.clc = (use_clc && cl == 2 && !tf32 && ctiles > max_cl) ? 1 : 0;
+        const int n_clusters = int(a.clc ? ctiles : (ctiles < max_cl ? ctiles : max_cl));
         return tf32 ? launch_pair_epi<OP_TF32>(tmA, tmB, a, n_clusters, pair_bn, cl, st)
                     : (op == OP_F16 ? launch_pair_epi<OP_F16>(tmA, tmB, a, n_clusters, pair_bn, cl, st)
                                     : launch_pair_epi<OP_BF16>(tmA, tmB, a, n_clusters, pair_bn, cl, st));

@@ -210,6 +210,29 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes) : "memory");
+}
+// Cluster launch control (CLC, sm_100): a resident cluster asks the hardware scheduler to CANCEL a cluster of its own grid that has not
+// been launched yet and takes over its work.  The 16-byte response lands at the same shared-memory offset in EVERY CTA of the cluster
+// and completes 16 bytes on the mbarrier at the same offset in each of them; clc_decode() -> blockIdx.x of the cancelled cluster's first
+// CTA, or -1 when nothing was left to cancel (after which no further request may be issued).
+__device__ __forceinline__ void clc_try_cancel_multicast(uint32_t resp_smem, uint32_t bar) {
+    asm volatile("clusterlaunchcontrol.try_cancel.async.shared::cta.mbarrier::complete_tx::bytes.multicast::cluster::all.b128 [%0], [%1];"
+                 ::"r"(resp_smem), "r"(bar) : "memory");
+}
+__device__ __forceinline__ int clc_decode(uint32_t resp_smem) {
+    uint32_t x, valid;
+    asm volatile(
+        "{\n\t.reg .pred p1;\n\t.reg .b128 r;\n\t"
+        "ld.shared.b128 r, [%2];\n\t"
+        "clusterlaunchcontrol.query_cancel.is_canceled.pred.b128 p1, r;\n\t"
+        "selp.u32 %1, 1, 0, p1;\n\t"
+        "mov.u32 %0, 0;\n\t"
+        "@p1 clusterlaunchcontrol.query_cancel.get_first_ctaid::x.b32.b128 %0, r;\n\t}"
+        : "=r"(x), "=r"(valid) : "r"(resp_smem) : "memory");
+    return valid ? int(x) : -1;
+}
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;      // clears the CTA-rank bit of a shared::cluster address -> the even (leader) CTA
 // 2D tile load issued by EITHER CTA of a pair into its own smem; the transaction bytes complete on the LEADER's mbarrier.
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst_smem, const CUtensorMap* m, uint32_t bar, int c0, int c1) {

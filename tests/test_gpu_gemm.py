@@ -132,3 +132,35 @@ def test_gemm_tf32(M, N, K):
     assert (out.double() - ref * (s * (1 + 1.702 * z.double() * (1 - s)))).abs().max() < 2 * tol
     outb = ops.gemm_tf32(a, w, ops.EPI_BIAS_BF16, bias=bias)
     assert outb.dtype == torch.bfloat16 and (outb.double() - pre).abs().max() < 2 ** -8 * float(pre.abs().max())
+
+
+@pytest.mark.parametrize("epi", [ops.EPI_BIAS_BF16, ops.EPI_BIAS_GELU_BF16, ops.EPI_BIAS_RESID_F32, ops.EPI_DGELU_BF16, ops.EPI_BF16])
+def test_gemm_one_row_per_sample(epi):
+    """M = batch size: the GEMMs of a tower's last block, which runs on the one row per sample the head reads (engine.Tower,
+    last_block_rows): a single, mostly empty 256-row tile per N tile."""
+    for M in (64, 5, 300):
+        _case(M, 768, 768, epi, 0, seed=11, half=torch.float16)
+        _case(M, 3072, 768, epi, 0, seed=12, half=torch.float16)
+        _case(M, 768, 3072, epi, 0, seed=13, half=torch.float16)
+
+
+def test_gemm_dynamic_tile_scheduler_clc():
+    """LPI_GEMM_CLC=1 (opt-in): one cluster per tile in the grid, the resident CTA pairs take over the tiles of the clusters that
+    have not been launched (clusterlaunchcontrol.try_cancel).  Same results as the static schedule; the switch is read once per
+    process, hence the child process."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import torch, tests.test_gpu_gemm as t\n"
+            "from lpi_b200 import ops\n"
+            "for epi in range(8):\n"
+            "    t._case(13632, 2304, 768, epi, 0, seed=21, half=torch.float16)\n"
+            "    t._case(13632, 768, 3072, epi, 0, seed=22)\n"
+            "    t._case(54528, 768, 768, epi, 1192, seed=23, half=torch.float16)\n"
+            "t._case(2496, 1536, 512, 0, 0, seed=24, half=torch.float16)\n"
+            "torch.cuda.synchronize(); print('clc-ok')\n")
+    env = dict(os.environ, LPI_GEMM_CLC="1", PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "clc-ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
