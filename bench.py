@@ -465,6 +465,15 @@ def run_b200(args):
             train = train_leg(dev, world, rank, group, max(3, min(args.steps, 10)), 3, peaks, args)
         except Exception as e:                       # the secondary leg must never take the headline line down
             train = {"error": repr(e)[:300]}
+    if train is not None and "error" not in train and not args.skip_train and args.train_batch == 64:
+        # BASELINE.json configs[2] spans batch 64 to 512: the same step at 256 pairs per GPU (timing + roofline only)
+        try:
+            torch.cuda.empty_cache()
+            t256 = train_leg(dev, world, rank, group, 5, 3, peaks, args, batch_per_gpu=256, light=True)
+            train["batch_256_per_gpu"] = {k: t256[k] for k in ("value", "unit", "ms_per_step", "global_batch", "launch_mode", "algorithmic_tflops",
+                                                                "executed_tflops", "roofline", "e2e") if k in t256}
+        except Exception as e:
+            train["batch_256_per_gpu"] = {"error": repr(e)[:300]}
     if rank == 0:
         line["train"] = train
         print(json.dumps(line), flush=True)
@@ -592,7 +601,7 @@ def _kernel_shares(step_fn, n_steps=2):
     return {k: {"ms": round(v, 4), "share": round(v / s, 4)} for k, v in sorted(tot.items(), key=lambda kv: -kv[1])}, s
 
 
-def train_leg(dev, world, rank, group, steps, warmup, peaks, args, batch_per_gpu=64):
+def train_leg(dev, world, rank, group, steps, warmup, peaks, args, batch_per_gpu=64, light=False):
     """Secondary metric of BASELINE.json ('prompted-CLIP train pairs/sec', configs[2]): COCO-shaped LPI training step, batch 64 per
     GPU, data-parallel over the ranks (global InfoNCE over all-gathered features, all-reduced prompt gradient), SGD step included."""
     import torch
@@ -620,7 +629,7 @@ def train_leg(dev, world, rank, group, steps, warmup, peaks, args, batch_per_gpu
 
     # ---- parity of the data-parallel step: the same global batch in ONE process on rank 0 (N > 1 only), before any SGD step
     parity = None
-    if world > 1:
+    if world > 1 and not light:
         r_dp = lpi_step.train_step(vision, text, fac0, images, tokens, 1 / 0.07, group=group, text_len=text_len)
         if rank == 0:
             gi = torch.cat([S.make_images(batch_per_gpu, r) for r in range(world)]).to(dev)
@@ -728,7 +737,7 @@ def train_leg(dev, world, rank, group, steps, warmup, peaks, args, batch_per_gpu
                        "gflop_per_pair": {"algorithmic": g_alg, "executed": g_exe}}
     if parity is not None:
         out["parity"] = parity
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and not light:
         try:                                               # where the step's time goes: event pairs around every kernel wrapper, eager, one stream
             shares, total = _kernel_shares(lambda: (lpi_step.train_step(vision, text, fac, images, tokens, 1 / 0.07, text_len=text_len,
                                                                         overlap_towers=False), None)[1])
@@ -739,7 +748,7 @@ def train_leg(dev, world, rank, group, steps, warmup, peaks, args, batch_per_gpu
             out["roofline"]["kernel_shares"] = {"error": repr(e)[:200]}
     del vision, text, graphed
     torch.cuda.empty_cache()
-    if rank == 0 and world == 1 and not args.skip_cpu:
+    if rank == 0 and world == 1 and not args.skip_cpu and not light:
         for leg in ("gpu-eager", "cpu-train-ref"):         # own processes: the CPU oracle patches torch.Tensor.cuda, the GPU leg must not see that
             try:
                 rr = subprocess.run([sys.executable, os.path.abspath(__file__), "--leg", leg, "--train-batch", str(batch_per_gpu)],

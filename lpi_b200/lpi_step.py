@@ -207,7 +207,14 @@ class GraphedTrainStep:
             self._copy_stream = torch.cuda.Stream(device=self.images.device)
             self._staged = None
         cs = self._copy_stream
-        cs.wait_stream(torch.cuda.current_stream())          # the previous step() has consumed the staging buffers
+        # the staging buffers are free once the previous step() has copied them into the captured inputs -- an event recorded right after
+        # those two device-to-device copies, NOT the end of the replay that follows them: waiting for the whole stream would put the PCIe
+        # copy (0.7 ms for a 64-image batch) between two steps instead of under one
+        consumed = getattr(self, "_consumed", None)
+        if consumed is not None:
+            cs.wait_event(consumed)
+        else:
+            cs.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(cs):
             self._stage[0].copy_(images, non_blocking=True)
             self._stage[1].copy_(tokens, non_blocking=True)
@@ -224,6 +231,8 @@ class GraphedTrainStep:
             self.images.copy_(self._stage[0], non_blocking=True)
             self.tokens.copy_(self._stage[1], non_blocking=True)
             self._staged = None
+            self._consumed = torch.cuda.Event()
+            self._consumed.record(torch.cuda.current_stream())
         if images is not None:
             self.images.copy_(images, non_blocking=True)
         if tokens is not None:

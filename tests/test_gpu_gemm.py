@@ -153,8 +153,9 @@ def test_gemm_dynamic_tile_scheduler_clc():
     import sys
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    code = ("import torch, tests.test_gpu_gemm as t\n"
-            "from lpi_b200 import ops\n"
+    code = ("import importlib.util, torch\n"
+            "spec = importlib.util.spec_from_file_location('gemm_cases', 'tests/test_gpu_gemm.py')\n"
+            "t = importlib.util.module_from_spec(spec); spec.loader.exec_module(t)\n"
             "for epi in range(8):\n"
             "    t._case(13632, 2304, 768, epi, 0, seed=21, half=torch.float16)\n"
             "    t._case(13632, 768, 3072, epi, 0, seed=22)\n"

@@ -24,7 +24,7 @@ for n in 5000000 625000; do
   ncu -i /tmp/scorer_full_$n.ncu-rep --page raw --csv > gpurun_out/scorer_full_raw_$n.csv 2>/dev/null
 done
 echo "== ncu full: one forward + one backward vision layer of the training step"
-timeout 900 ncu --set full --clock-control none -k regex:"gemm_pair|attn_|layernorm" -s 420 -c 10 -f -o /tmp/train_fwd python tools/bench_train.py --batch 64 --steps 1 --warmup 2 > gpurun_out/ncu_train_fwd.log 2>&1
+timeout 900 ncu --set full --clock-control none -k regex:"gemm_pair|attn_|layernorm" -s 470 -c 10 -f -o /tmp/train_fwd python tools/bench_train.py --batch 64 --steps 1 --warmup 2 > gpurun_out/ncu_train_fwd.log 2>&1
 ncu -i /tmp/train_fwd.ncu-rep --page raw --csv > gpurun_out/train_fwd_raw.csv 2>/dev/null
 timeout 900 ncu --set full --clock-control none -k regex:"gemm_pair|attn_|layernorm" -s 640 -c 12 -f -o /tmp/train_bwd python tools/bench_train.py --batch 64 --steps 1 --warmup 2 > gpurun_out/ncu_train_bwd.log 2>&1
 ncu -i /tmp/train_bwd.ncu-rep --page raw --csv > gpurun_out/train_bwd_raw.csv 2>/dev/null
