@@ -340,6 +340,9 @@ __global__ void inject_prompt_rows_kernel(float* __restrict__ x, const float* __
 // slice of the projection for them with the D-long reduction split over its 8 warps (partials combined through smem); the L2
 // normalisation over E follows in head_norm_kernel.
 constexpr int HB = 8;
+// KC = projection rows whose loads are in flight together (32 when the per-warp span allows: three L2 round trips per warp at D = 768
+// instead of twelve -- this kernel sits on the serial stretch between the towers' forward and backward)
+template <int KC>
 __global__ void __launch_bounds__(256)
 head_fwd_kernel(const float* __restrict__ x, const int* __restrict__ row_idx, const float* __restrict__ gamma, const float* __restrict__ beta,
                 const float* __restrict__ proj, float* __restrict__ z_out, int B, int D, int E, float eps) {
@@ -367,12 +370,12 @@ head_fwd_kernel(const float* __restrict__ x, const int* __restrict__ row_idx, co
     for (int h = 0; h < HB; ++h) acc[h] = 0.f;
     if (e < E) {
         const int kspan = D / 8;                     // D % 64 == 0 for every supported width
-        for (int k0 = warp * kspan; k0 < (warp + 1) * kspan; k0 += 8) {
-            float w[8];
+        for (int k0 = warp * kspan; k0 < (warp + 1) * kspan; k0 += KC) {
+            float w[KC];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) w[i] = __ldg(proj + long(k0 + i) * E + e);
+            for (int i = 0; i < KC; ++i) w[i] = __ldg(proj + long(k0 + i) * E + e);
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int i = 0; i < KC; ++i)
 #pragma unroll
                 for (int h = 0; h < HB; ++h) acc[h] = fmaf(y[h * D + k0 + i], w[i], acc[h]);
         }
@@ -457,6 +460,37 @@ head_bwd_dy_kernel(const float* __restrict__ dfeat, const float* __restrict__ dz
     }
     __syncthreads();
     const int k_end = min(D, (blockIdx.y + 1) * 64);
+    if (E == 512) {
+        // the usual width: the 16 loads of a projection row are issued together, and the next row's before this row's reductions
+        float w[16], wn[16];
+        int k = blockIdx.y * 64 + warp;
+        if (k < k_end) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) w[i] = __ldg(proj + long(k) * E + lane + 32 * i);
+        }
+        for (; k < k_end; k += 8) {
+            const bool more = k + 8 < k_end;
+            if (more) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) wn[i] = __ldg(proj + long(k + 8) * E + lane + 32 * i);
+            }
+            float acc[HBB];
+#pragma unroll
+            for (int h = 0; h < HBB; ++h) acc[h] = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+#pragma unroll
+                for (int h = 0; h < HBB; ++h) acc[h] = fmaf(sm[h * E + lane + 32 * i], w[i], acc[h]);
+#pragma unroll
+            for (int h = 0; h < HBB; ++h) {
+                const float v = warp_sum(acc[h]);
+                if (lane == 0 && b0 + h < B) g[long(row_idx[b0 + h]) * D + k] = v;
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) w[i] = wn[i];
+        }
+        return;
+    }
     for (int k = blockIdx.y * 64 + warp; k < k_end; k += 8) {          // dy[b, k] = sum_e dz[b, e] proj[k, e]
         float acc[HBB];
 #pragma unroll
@@ -720,7 +754,8 @@ extern "C" int lpi_head_fwd(const float* x, const int* row_idx, const float* ln_
     const int smem = (HB * D + 8 * HB * 32) * sizeof(float);
     if (smem > 48 * 1024) return set_error(LPI_ERR_UNSUPPORTED, "head_fwd: D=%d too wide", D);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    head_fwd_kernel<<<dim3((B + HB - 1) / HB, (E + 31) / 32), 256, smem, st>>>(x, row_idx, ln_gamma, ln_beta, proj, z_out, B, D, E, eps);
+    if ((D / 8) % 32 == 0) head_fwd_kernel<32><<<dim3((B + HB - 1) / HB, (E + 31) / 32), 256, smem, st>>>(x, row_idx, ln_gamma, ln_beta, proj, z_out, B, D, E, eps);
+    else head_fwd_kernel<8><<<dim3((B + HB - 1) / HB, (E + 31) / 32), 256, smem, st>>>(x, row_idx, ln_gamma, ln_beta, proj, z_out, B, D, E, eps);
     head_norm_kernel<<<(B * 32 + 255) / 256, 256, 0, st>>>(z_out, feat_out, B, E);
     return check_launch("head_fwd");
 }
@@ -734,7 +769,8 @@ extern "C" int lpi_head_fwd_select(const float* x, const int* row_idx, const flo
     const int smem = (HB * D + 8 * HB * 32) * sizeof(float);
     if (smem > 48 * 1024) return set_error(LPI_ERR_UNSUPPORTED, "head_fwd_select: D=%d too wide", D);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    head_fwd_kernel<<<dim3((B + HB - 1) / HB, (E + 31) / 32), 256, smem, st>>>(x, row_idx, ln_gamma, ln_beta, proj, z_out, B, D, E, eps);
+    if ((D / 8) % 32 == 0) head_fwd_kernel<32><<<dim3((B + HB - 1) / HB, (E + 31) / 32), 256, smem, st>>>(x, row_idx, ln_gamma, ln_beta, proj, z_out, B, D, E, eps);
+    else head_fwd_kernel<8><<<dim3((B + HB - 1) / HB, (E + 31) / 32), 256, smem, st>>>(x, row_idx, ln_gamma, ln_beta, proj, z_out, B, D, E, eps);
     head_norm_select_kernel<<<(B * 32 + 255) / 256, 256, 0, st>>>(z_out, feat_out, centers, n_tasks, n_centers, sel_out, B, E);
     return check_launch("head_fwd_select");
 }
