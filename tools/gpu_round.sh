@@ -17,8 +17,8 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"
   --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --skip-cpu --skip-train --skip-sweep > gpurun_out/ncu_launches.log 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 1250 -c 850 --csv --log-file gpurun_out/train_launches.csv \
   python tools/bench_train.py --batch 64 --steps 2 --warmup 3 > gpurun_out/ncu_train.log 2>&1
-echo "== ncu full: scorer main pass at 5 M rows (N = 1) and at the 625 k-row shard of the 8-GPU run"
-for n in 5000000 625000; do
+echo "== ncu full: scorer main pass at 5 M rows (N = 1) and at the shards of the 2 / 4 / 8-GPU runs"
+for n in 5000000 2500000 1250000 625000; do
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_pair -s 7 -c 1 -f -o /tmp/scorer_full_$n \
     python bench.py --gallery $n --steps 1 --warmup 3 --skip-cpu --skip-train --skip-sweep > gpurun_out/ncu_full_$n.log 2>&1
   ncu -i /tmp/scorer_full_$n.ncu-rep --page raw --csv > gpurun_out/scorer_full_raw_$n.csv 2>/dev/null

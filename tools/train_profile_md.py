@@ -70,7 +70,7 @@ if __name__ == "__main__":
     d = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out"
     print("## Launch list (`ncu --metrics gpu__time_duration.sum --clock-control none -s 1250 -c 850 python tools/bench_train.py --batch 64 --steps 2 --warmup 3`)\n")
     print(launch_table(f"{d}/train_launches.csv"))
-    print("\n## ncu `--set full` over a forward stretch (`-k regex:gemm_pair|attn_|layernorm -s 420 -c 10`)\n")
+    print("\n## ncu `--set full` over a forward stretch (`-k regex:gemm_pair|attn_|layernorm -s 470 -c 10`)\n")
     print(full_table(f"{d}/train_fwd_raw.csv"))
     print("\n## ncu `--set full` over a backward stretch (`-s 640 -c 12`)\n")
     print(full_table(f"{d}/train_bwd_raw.csv"))
