@@ -636,17 +636,11 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQKV, const __grid_const
 // 3-D view [B, L, cols] of a row-major [B*L, cols] bf16 matrix, box = [1, box_rows, 64 columns], SWIZZLE_128B;
 // rows past L (and past B) are zero-filled, so a tile never sees the next sample's tokens.
 static int make_tmap_rows3d(CUtensorMap* m, const void* ptr, int B, int L, int cols, int box_rows, bool f16 = false) {
-    if (int rc = ensure_tma_encoder()) return rc;
     if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (cols % 8)) return set_error(LPI_ERR_ARG, "attention: operand must be 16-byte aligned");
-    const PFN_encodeTiled enc = tma_encoder();
     cuuint64_t dims[3] = {cuuint64_t(cols), cuuint64_t(L), cuuint64_t(B)};
     cuuint64_t strides[2] = {cuuint64_t(cols) * 2, cuuint64_t(L) * cols * 2};
     cuuint32_t box[3] = {64, cuuint32_t(box_rows), 1};
-    cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return set_error(LPI_ERR_CUDA, "attention: cuTensorMapEncodeTiled failed: %d", int(r));
-    return 0;
+    return make_tmap_cached(m, ptr, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, dims, strides, box);
 }
 
 bool attn_tc_enabled(int L) {

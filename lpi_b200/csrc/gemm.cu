@@ -17,6 +17,7 @@
 //                   of its query row ordered by (score desc, gallery index asc).
 #include "ptx.cuh"
 #include "lpi_internal.h"
+#include <string.h>
 #include <cuda_fp16.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -1268,9 +1269,49 @@ int ensure_tma_encoder() {
 PFN_encodeTiled tma_encoder() { return g_encode; }      // valid after ensure_tma_encoder()
 
 // 2D row-major [rows, cols] tensor map with a [box_rows, box_cols] box, SWIZZLE_128B.
+// A tensor map is a pure function of (base pointer, element type, extents, strides, box): the encoded descriptors are kept in a small
+// per-thread direct-mapped cache, so the eager path (one Python thread issuing ~400 launches per training step, weights and the
+// caching allocator's activation buffers at the same addresses every step) stops paying two or three cuTensorMapEncodeTiled calls per
+// kernel; graph replays never reach this code.  SWIZZLE_128B, no interleave, 256 B L2 promotion, zero fill -- as every kernel here uses.
+int make_tmap_cached(CUtensorMap* m, const void* ptr, CUtensorMapDataType dt, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                     const cuuint32_t* box) {
+    if (int rc = ensure_tma_encoder()) return rc;
+    struct Entry {
+        const void* ptr;
+        cuuint64_t dims[3], strides[2];
+        cuuint32_t box[3];
+        int dt, rank;
+        bool valid;
+        CUtensorMap map;
+    };
+    constexpr int kSlots = 1024;
+    static thread_local Entry* cache = nullptr;
+    if (!cache) cache = new Entry[kSlots]();
+    Entry key{};
+    key.ptr = ptr; key.dt = int(dt); key.rank = rank;
+    for (int i = 0; i < rank; ++i) { key.dims[i] = dims[i]; key.box[i] = box[i]; }
+    for (int i = 0; i + 1 < rank; ++i) key.strides[i] = strides[i];
+    uint64_t h = reinterpret_cast<uintptr_t>(ptr) * 0x9E3779B97F4A7C15ull;
+    for (int i = 0; i < 3; ++i) h = (h ^ key.dims[i] ^ (uint64_t(key.box[i]) << 40)) * 0xFF51AFD7ED558CCDull;
+    h ^= key.strides[0] * 31 + key.strides[1] * 131 + uint64_t(key.dt) * 7 + uint64_t(rank);
+    Entry& e = cache[(h >> 17) & (kSlots - 1)];
+    if (e.valid && e.ptr == key.ptr && e.dt == key.dt && e.rank == key.rank && !memcmp(e.dims, key.dims, sizeof(key.dims)) &&
+        !memcmp(e.strides, key.strides, sizeof(key.strides)) && !memcmp(e.box, key.box, sizeof(key.box))) {
+        *m = e.map;
+        return 0;
+    }
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_encode(m, dt, cuuint32_t(rank), const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(LPI_ERR_CUDA, "cuTensorMapEncodeTiled failed: %d", int(r));
+    key.valid = true;
+    key.map = *m;
+    e = key;
+    return 0;
+}
+
 int make_tmap_2d(CUtensorMap* m, const void* ptr, CUtensorMapDataType dt, int elem_bytes, uint64_t rows, uint64_t cols,
                  uint64_t ld_elems, uint32_t box_rows, uint32_t box_cols) {
-    if (int rc = ensure_tma_encoder()) return rc;
     if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld_elems * elem_bytes) & 15))
         return set_error(LPI_ERR_ARG, "TMA operand must be 16-byte aligned (ptr=%p ld=%llu)", ptr, (unsigned long long)ld_elems);
     if (box_cols * elem_bytes != 128 || box_rows > 256)
@@ -1278,11 +1319,7 @@ int make_tmap_2d(CUtensorMap* m, const void* ptr, CUtensorMapDataType dt, int el
     cuuint64_t dims[2] = {cols, rows};
     cuuint64_t strides[1] = {ld_elems * elem_bytes};
     cuuint32_t box[2] = {box_cols, box_rows};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = g_encode(m, dt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return set_error(LPI_ERR_CUDA, "cuTensorMapEncodeTiled failed: %d", int(r));
-    return 0;
+    return make_tmap_cached(m, ptr, dt, 2, dims, strides, box);
 }
 
 static int g_num_sms = 0;

@@ -17,6 +17,8 @@ int check_launch(const char* what);              // cudaGetLastError -> error co
 int num_sms();
 int ensure_tma_encoder();
 PFN_encodeTiled tma_encoder();                    // cuTensorMapEncodeTiled entry point (after ensure_tma_encoder() returned 0)
+int make_tmap_cached(CUtensorMap* m, const void* ptr, CUtensorMapDataType dt, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                     const cuuint32_t* box);       // SWIZZLE_128B tiled map of rank 2 or 3, memoised per thread
 int make_tmap_2d(CUtensorMap* m, const void* ptr, CUtensorMapDataType dt, int elem_bytes, uint64_t rows, uint64_t cols,
                  uint64_t ld_elems, uint32_t box_rows, uint32_t box_cols);
 
