@@ -63,6 +63,15 @@ int lpi_gemm_tf32(const void* A, const void* B, int M, int N, int K, int epi, co
 int lpi_gemm_f16(const void* A, const void* B, int M, int N, int K, int epi, const void* bias_f32, const void* resid_f32,
                  void* out, void* out2, const void* aux_f16, int ldo, int tile_n, void* stream);
 
+/* out_proj dgrad fused with the attention backward's delta (autograd of nn.MultiheadAttention, models/clip/model.py:172,183-185):
+ *   out[M, N] (16-bit) = A[M, K] . Wt[N, K]^T                      -- d loss / d (attention output), what lpi_gemm_* EPI_BF16 computes
+ *   delta[b, h, l]    += sum_{d < 64} acc_fp32[b*L + l, 64 h + d] * o_saved[b*L + l, 64 h + d]
+ * i.e. the row sums the softmax backward needs, taken from the fp32 accumulator in the epilogue (thread = row; two atomic adds per
+ * (row, head) onto the caller-ZEROED delta [M/L, N/64, L], so the sum does not depend on their order).  Replaces one pass over dO and O
+ * per block.  M % L == 0, N % 64 == 0; f16: 0 = bf16 operands / outputs, 1 = fp16. */
+int lpi_gemm_do_delta(const void* A, const void* Wt, int M, int N, int K, void* out, const void* o_saved, float* delta, int L, int f16,
+                      void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Retrieval scorer: similarity GEMM with the top-k kept in the epilogue (score matrix never written).
  * replaces: `score_matrix_t2i = (image_feats @ text_feats.t()).t()` + D2H + per-row np.argsort,
@@ -127,6 +136,8 @@ int lpi_l2_normalize(const float* x, int n, int dim, float* out, float* norm_out
  *           (+ the causal mask built at model.py:347-353) and its autograd backward.
  * qkv [B*L, 3*H*64] bf16 (row = b*L + l; columns q | k | v), out / d_out [B*L, H*64] bf16, lse2 [B*H*L] fp32
  * (log2-domain log-sum-exp saved by the forward for the backward), delta_ws [B*H*L] fp32 scratch, dqkv like qkv.
+ * lpi_attn_bwd / lpi_attn_bwd_f16 with out == NULL: delta_ws is an INPUT holding delta[b,h,l] = sum_d d_out * out, as lpi_gemm_do_delta
+ * leaves it (no separate delta pass).
  * ------------------------------------------------------------------------------------------------ */
 int lpi_attn_fwd(const void* qkv, void* out, float* out_f32 /* optional fp32 copy of out */, float* lse2, int B, int L, int H,
                  int causal, void* stream);

@@ -460,7 +460,8 @@ extern "C" int lpi_attn_bwd(const void* qkv, const void* out, const void* d_out,
     auto d_o = static_cast<const __nv_bfloat16*>(d_out);
     auto dq = static_cast<__nv_bfloat16*>(dqkv);
     const long rows = long(B) * L;
-    launch_pdl(attn_delta_kernel<false>, dim3(unsigned((rows * 32 + 255) / 256)), dim3(256), 0, st, o, d_o, delta_ws, B, L, H);
+    // out == NULL: delta_ws already holds rowsum(dO o O) (lpi_gemm_do_delta computed it in the epilogue of the out_proj dgrad)
+    if (o) launch_pdl(attn_delta_kernel<false>, dim3(unsigned((rows * 32 + 255) / 256)), dim3(256), 0, st, o, d_o, delta_ws, B, L, H);
     if (attn_tc_enabled(L)) return attn_bwd_tc(qkv, d_out, lse2, delta_ws, dqkv, dqkv_f32, B, L, H, causal, false, st);
     const dim3 grid((L + QB - 1) / QB, H, B);
     if (causal) {
@@ -491,7 +492,8 @@ extern "C" int lpi_attn_bwd_f16(const void* qkv, const void* out, const void* d_
     if (!dqkv) return set_error(LPI_ERR_ARG, "attn_bwd_f16: no output");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long rows = long(B) * L;
-    launch_pdl(attn_delta_kernel<true>, dim3(unsigned((rows * 32 + 255) / 256)), dim3(256), 0, st, static_cast<const __nv_bfloat16*>(out),
-               static_cast<const __nv_bfloat16*>(d_out), delta_ws, B, L, H);
+    if (out)      // NULL: delta_ws already holds rowsum(dO o O) (lpi_gemm_do_delta)
+        launch_pdl(attn_delta_kernel<true>, dim3(unsigned((rows * 32 + 255) / 256)), dim3(256), 0, st, static_cast<const __nv_bfloat16*>(out),
+                   static_cast<const __nv_bfloat16*>(d_out), delta_ws, B, L, H);
     return attn_bwd_tc(qkv, d_out, lse2, delta_ws, dqkv, nullptr, B, L, H, causal, true, st);
 }

@@ -64,6 +64,8 @@ struct GemmArgs {
     const float* aux_f32;          // [M, ldo] fp32 pre-activation (EPI_DGELU_F32)
     int ldo;
     int probe;                     // only in -DLPI_DEBUG_PROBE builds (tools/gemm_probe.py): 1 = the pair GEMM skips its A-tile loads (WRONG results, timing study)
+    float* delta;                  // EPI_BF16 of the out_proj dgrad: delta[b, h, l] += rowsum over head h of out(fp32) * aux (aux = the saved attention
+    int delta_L;                   //   output O [M, N], N = 64 H, row = b * delta_L + l); delta [M / L * H * L] is zeroed by the caller (lpi_gemm_do_delta)
     int clc;                       // pair GEMM: 1 = one cluster per tile in the grid, resident clusters steal the pending ones (cluster launch control)
     int precise_act;               // fp16 outputs: 1 = ex2 + rcp sigmoid (2 MUFU ops), 0 = tanh.approx (1 MUFU op, |err| <= 2^-12)
     // MODE_TOPK
@@ -1134,6 +1136,14 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     prefetch_resid_block(p, m0 + quad * 32, n0 + (col_half * NCH + 0) * 32, lane, rs0);
                     prefetch_resid_block(p, m0 + quad * 32, n0 + (col_half * NCH + 1) * 32, lane, rs1);
                 }
+                // out_proj dgrad with the attention backward's delta fused (p.delta): this thread's row of the saved attention output O for
+                // every 32-column block the warp drains, requested before the accumulator wait (one 64-byte segment per block)
+                constexpr bool kDelta = (MODE == MODE_GEMM) && (EPI == EPI_BF16) && !TF32;
+                uint32_t od[kDelta ? NCH : 1][16];
+                if (kDelta && p.delta != nullptr) {
+#pragma unroll
+                    for (int cc = 0; cc < NCH; ++cc) prefetch_aux_direct(p, row, n0 + (col_half * NCH + cc) * 32, valid, od[kDelta ? cc : 0]);
+                }
                 mbar_wait(tfull_bar(acc), acc_phase);
                 tc_fence_after();
                 if (MODE == MODE_GEMM && LPI_EPI_DIRECT) {
@@ -1153,7 +1163,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                     if (NCH > 2) block(cb + 2, d0);
                     if (NCH > 3) block(cb + 3, d1);
                 } else if (MODE == MODE_GEMM) {
-                    auto do_block = [&](int c, const uint2* pre, const float4* pre_rs = nullptr) {
+                    auto do_block = [&](int c, const uint2* pre, const float4* pre_rs = nullptr, int dl = 0) {
 #if defined(LPI_DEBUG_PROBE) && LPI_DEBUG_PROBE == 2
                         return;                                // timing study: no epilogue at all (results WRONG)
 #endif
@@ -1165,6 +1175,21 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         if (r[0] == 0x7fc01234u && r[31] == 0x7fc04321u) p.out_f32[0] = 1.f;      // timing study: TMEM drain only (results WRONG)
                         return;
 #endif
+                        if (kDelta && p.delta != nullptr && valid) {
+                            // delta[b, h, l] += sum over these 32 columns of dO (fp32 accumulator) * O: two addends per (row, head) on a
+                            // zeroed buffer, so the result does not depend on their order
+                            const uint32_t* o = od[kDelta ? dl : 0];
+                            float dsum = 0.f;
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                const float2 of = F16 ? __half22float2(*reinterpret_cast<const __half2*>(&o[j]))
+                                                      : __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&o[j]));
+                                dsum = fmaf(__uint_as_float(r[2 * j]), of.x, dsum);
+                                dsum = fmaf(__uint_as_float(r[2 * j + 1]), of.y, dsum);
+                            }
+                            const int bb = row / p.delta_L, ll = row - bb * p.delta_L, hh = (n0 + c * 32) >> 6;
+                            atomicAdd(p.delta + (size_t(bb) * (p.N >> 6) + hh) * p.delta_L + ll, dsum);
+                        }
                         float4* stg = reinterpret_cast<float4*>(smem_gen + C::LIST_OFF) + (warp - 2) * 32 * 8;
                         constexpr bool k16 = (EPI == EPI_BIAS_BF16 || EPI == EPI_BF16 || EPI == EPI_BIAS_GELU_BF16) && LPI_EPI16;
                         if (k16) {
@@ -1197,8 +1222,13 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         if (NCH > 2) do_block(cb + 2, nullptr, rs0);
                         if (NCH > 3) do_block(cb + 3, nullptr, rs1);
                     } else {
+                        if (kDelta) {                  // unrolled: the prefetched O segments are indexed statically
+#pragma unroll
+                            for (int cc = 0; cc < NCH; ++cc) do_block(col_half * NCH + cc, nullptr, nullptr, cc);
+                        } else {
 #pragma unroll 1
-                        for (int c = col_half * NCH; c < (col_half + 1) * NCH; ++c) do_block(c, nullptr);
+                            for (int c = col_half * NCH; c < (col_half + 1) * NCH; ++c) do_block(c, nullptr);
+                        }
                     }
                 } else {
                     float tmax = -INFINITY;
@@ -1456,6 +1486,9 @@ static int launch_epi_tf32(const CUtensorMap& tmA, const CUtensorMap& tmB, const
 
 using namespace lpi;
 
+static thread_local float* g_delta_out;
+static thread_local int g_delta_L;
+
 static int gemm_entry(int op, const void* A, const void* B, int M, int N, int K, int epi, const void* bias, const void* resid,
                       void* out, void* out2, const void* aux, int ldo, int tile_n, void* stream) {
     const bool tf32 = op == OP_TF32;
@@ -1533,6 +1566,8 @@ static int gemm_entry(int op, const void* A, const void* B, int M, int N, int K,
     }
     a.bias = static_cast<const float*>(bias);
     a.resid = static_cast<const float*>(resid);
+    a.delta = (epi == EPI_BF16) ? g_delta_out : nullptr;
+    a.delta_L = g_delta_L;
     if (epi == EPI_DGELU_F32) a.aux_f32 = static_cast<const float*>(aux);
     else a.aux_bf16 = static_cast<const __nv_bfloat16*>(aux);
     if (epi == EPI_BIAS_GELU_F32) a.out2_f32 = static_cast<float*>(out2);
@@ -1573,6 +1608,18 @@ static int gemm_entry(int op, const void* A, const void* B, int M, int N, int K,
     const int grid = int(tiles < sms ? tiles : sms);
     if (tf32) return bn == 256 ? launch_epi_tf32<256>(tmA, tmB, a, grid, st) : launch_epi_tf32<128>(tmA, tmB, a, grid, st);
     return bn == 256 ? launch_epi<256>(tmA, tmB, a, grid, st) : launch_epi<128>(tmA, tmB, a, grid, st);
+}
+
+// out_proj dgrad (EPI_BF16) with the attention backward's delta fused into the epilogue -- see include/lpi_b200.h
+extern "C" int lpi_gemm_do_delta(const void* A, const void* Wt, int M, int N, int K, void* out, const void* o_saved, float* delta, int L, int f16,
+                                 void* stream) {
+    if (!o_saved || !delta || L <= 0 || (M % L) || (N % 64)) return set_error(LPI_ERR_ARG, "gemm_do_delta: need O, delta, M %% L == 0, N %% 64 == 0 (M=%d L=%d N=%d)", M, L, N);
+    g_delta_out = delta;
+    g_delta_L = L;
+    const int rc = gemm_entry(f16 ? OP_F16 : OP_BF16, A, Wt, M, N, K, EPI_BF16, nullptr, nullptr, out, nullptr, o_saved, N, 0, stream);
+    g_delta_out = nullptr;
+    g_delta_L = 0;
+    return rc;
 }
 
 extern "C" int lpi_gemm_bf16(const void* A, const void* B, int M, int N, int K, int epi, const void* bias, const void* resid, void* out,

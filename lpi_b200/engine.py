@@ -125,6 +125,9 @@ class Tower:
         # instead of [B*L, D]; the rows that are skipped reach neither the features nor any gradient.  LPI_LAST_BLOCK_FULL=1 (or
         # last_block_rows = False) runs the full block instead; the tf32 / fp32 study modes always do.
         self.last_block_rows = os.environ.get("LPI_LAST_BLOCK_FULL") != "1" and not self.tf32
+        # backward: the out_proj dgrad GEMM also produces the attention backward's delta = rowsum(dO o O) in its epilogue
+        # (ops.gemm_do_delta) instead of a separate pass over dO and O per block; LPI_FUSED_DELTA=0 runs the separate kernel
+        self.fuse_delta = os.environ.get("LPI_FUSED_DELTA", "1") != "0"
 
     # -------------------------------------------------------------------------------------------- forward
     def forward(self, x: torch.Tensor, B: int, L: int, tape: Optional[TowerTape] = None,
@@ -233,11 +236,22 @@ class Tower:
         B, L, H = tape.B, tape.L, self.heads
         if self.tf32:
             return self._backward_tf32(tape, g, inject, inject_grads)
+        fuse_delta = self.fuse_delta and L <= 256
+        delta_pool = torch.zeros(len(self.blocks), B * H * L, device=g.device, dtype=torch.float32) if fuse_delta else None
         for li in range(len(self.blocks) - 1, -1, -1):
             w, s = self.blocks[li], tape.blocks[li]
             dz = ops.gemm(g_bf16, w.w_proj_t, ops.EPI_DGELU_BF16, aux=s.z)
             dh2 = ops.gemm(dz, w.w_fc_t, self.epi_dh)
             ops.layernorm_bwd(dh2, s.x1, w.ln2_g, g, g_bf16, accumulate=True, grad_scale=self.grad_scale)
+            rows_only = tape.out_rows is not None and li == len(self.blocks) - 1
+            if fuse_delta and not rows_only:
+                do = ops.gemm_do_delta(g_bf16, w.w_out_t, s.o, delta_pool[li], L)
+                dqkv = ops.attn_bwd(s.qkv, None, do, s.lse, B, L, H, self.causal, delta=delta_pool[li])
+                dh1 = ops.gemm(dqkv, w.w_in_t, self.epi_dh)
+                ops.layernorm_bwd(dh1, s.x, w.ln1_g, g, g_bf16, accumulate=True, grad_scale=self.grad_scale)
+                if inject is not None and li != 0 and li in inject["layers"] and inject_grads is not None:
+                    inject_grads[li] = ops.sum_prompt_rows(g, inject["sel"], B, L, inject["P"], inject["table"].shape[0], self.width)
+                continue
             do = ops.gemm(g_bf16, w.w_out_t, ops.EPI_BF16)
             if tape.out_rows is not None and li == len(self.blocks) - 1:
                 # the last block ran on the read rows: g / g_bf16 are [B, D] up to here; dk / dv of every position (and dq of the read

@@ -61,6 +61,25 @@ def gemm(a: torch.Tensor, w: torch.Tensor, epi: int, bias: Optional[torch.Tensor
     return out
 
 
+def gemm_do_delta(a: torch.Tensor, w: torch.Tensor, o_saved: torch.Tensor, delta: torch.Tensor, L: int) -> torch.Tensor:
+    """out_proj dgrad with the attention backward's delta fused (lpi_gemm_do_delta): -> d_out [M, N] (a's dtype); delta (fp32, ZEROED
+    by the caller, [M / L * N / 64 * L]) receives rowsum_head(d_out * o_saved)."""
+    _lib.require_device()
+    h = a.dtype
+    if h not in (torch.bfloat16, torch.float16):
+        raise _lib.LpiError(f"a must be bf16 or fp16, got {a.dtype}")
+    for t, n in ((a, "a"), (w, "w"), (o_saved, "o_saved")):
+        _chk(t, h, n)
+    _chk(delta, torch.float32, "delta")
+    M, K = a.shape
+    N = w.shape[0]
+    assert w.shape[1] == K and o_saved.shape == (M, N) and delta.numel() == (M // L) * (N // 64) * L
+    out = torch.empty(M, N, device=a.device, dtype=h)
+    call("gemm_do_delta", ptr(a), ptr(w), M, N, K, ptr(out), ptr(o_saved), ptr(delta), L, int(h == torch.float16), stream_ptr())
+    _count()
+    return out
+
+
 def gemm_tf32(a: torch.Tensor, w: torch.Tensor, epi: int, bias: Optional[torch.Tensor] = None, resid: Optional[torch.Tensor] = None,
               out: Optional[torch.Tensor] = None, out2: Optional[torch.Tensor] = None, aux: Optional[torch.Tensor] = None,
               tile_n: int = 0) -> torch.Tensor:
@@ -356,25 +375,33 @@ def attn_fwd(qkv: torch.Tensor, B: int, L: int, H: int, causal: bool, want_lse: 
     return (out, lse, of) if want_f32 else (out, lse)
 
 
-def attn_bwd(qkv, out, d_out, lse, B: int, L: int, H: int, causal: bool, dqkv: Optional[torch.Tensor] = None, f32: bool = False):
+def attn_bwd(qkv, out, d_out, lse, B: int, L: int, H: int, causal: bool, dqkv: Optional[torch.Tensor] = None, f32: bool = False,
+             delta: Optional[torch.Tensor] = None):
+    """delta given (fp32 [B*H*L], from gemm_do_delta): `out` is not read and no separate delta pass runs."""
     h = qkv.dtype
-    for t, n in ((qkv, "qkv"), (out, "out"), (d_out, "d_out")):
+    for t, n in ((qkv, "qkv"), (d_out, "d_out")) + (((out, "out"),) if delta is None else ()):
         _chk(t, h, n)
     _chk(lse, torch.float32, "lse")
-    delta = torch.empty(B * H * L, device=qkv.device, dtype=torch.float32)
+    given = delta is not None
+    if given:
+        _chk(delta, torch.float32, "delta")
+        assert delta.numel() == B * H * L
+        out = None
+    else:
+        delta = torch.empty(B * H * L, device=qkv.device, dtype=torch.float32)
     if h == torch.float16:
         if f32:
             raise _lib.LpiError("attn_bwd: the fp16 path writes fp16 gradients")
         if dqkv is None:
             dqkv = torch.empty_like(qkv)
         call("attn_bwd_f16", ptr(qkv), ptr(out), ptr(d_out), ptr(lse), ptr(delta), ptr(dqkv), B, L, H, int(causal), stream_ptr())
-        _count(2)
+        _count(1 if given else 2)
         return dqkv
     if dqkv is None:
         dqkv = torch.empty_like(qkv, dtype=torch.float32 if f32 else torch.bfloat16)
     call("attn_bwd", ptr(qkv), ptr(out), ptr(d_out), ptr(lse), ptr(delta), None if f32 else ptr(dqkv), ptr(dqkv) if f32 else None, B, L, H,
          int(causal), stream_ptr())
-    _count(2 if L <= 256 else 3)
+    _count((2 if L <= 256 else 3) - (1 if given else 0))
     return dqkv
 
 

@@ -165,3 +165,26 @@ def test_gemm_dynamic_tile_scheduler_clc():
     env = dict(os.environ, LPI_GEMM_CLC="1", PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
     r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "clc-ok" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("B,L,H,K,half", [(64, 213, 12, 768, torch.float16), (3, 39, 8, 512, torch.float16), (5, 77, 8, 512, torch.bfloat16),
+                                          (2, 197, 12, 768, torch.bfloat16), (1, 1, 2, 64, torch.float16)])
+def test_gemm_do_delta(B, L, H, K, half):
+    """lpi_gemm_do_delta: the out_proj dgrad (EPI_BF16) whose epilogue also leaves delta[b, h, l] = sum_d dO * O, the row sums of the
+    attention backward (model.py:172,183-185 under autograd), on the caller-zeroed buffer; every cluster tile width."""
+    g = torch.Generator().manual_seed(B * 7 + L)
+    M, N = B * L, H * 64
+    a = torch.randn(M, K, generator=g).cuda().to(half)
+    w = (torch.randn(N, K, generator=g) * K ** -0.5).cuda().to(half)
+    o = torch.randn(M, N, generator=g).cuda().to(half)
+    delta = torch.zeros(B * H * L, device="cuda")
+    out = ops.gemm_do_delta(a, w, o, delta, L)
+    ref = a.float() @ w.float().t()
+    hr = 2 ** -8 if half == torch.bfloat16 else 2 ** -10
+    assert out.dtype == half and (out.float() - ref).abs().max() <= hr * max(1.0, ref.abs().max().item())
+    assert torch.equal(out, ops.gemm(a, w, ops.EPI_BF16))                      # the GEMM result itself is unchanged
+    want = (ref * o.float()).view(B, L, H, 64).sum(-1).permute(0, 2, 1).reshape(-1)
+    assert (delta - want).abs().max() <= 2e-5 * max(1.0, want.abs().max().item()) + 1e-4
+    delta2 = torch.zeros_like(delta)
+    ops.gemm_do_delta(a, w, o, delta2, L)
+    assert torch.equal(delta, delta2)                                          # two addends per element: order-independent

@@ -269,3 +269,25 @@ def test_last_block_on_read_rows_equals_the_full_block(engines):
             (f0, z0, G0, e0), (f1, z1, G1, e1) = res
             assert _rel(f1, f0) < 1e-3 and _rel(z1, z0) < 1e-3 and _rel(e1, f1) < 1e-6 and _rel(e0, f0) < 1e-6
             assert _rel(G1, G0) < 5e-3, (type(eng).__name__, inject, _rel(G1, G0))
+
+
+def test_fused_delta_equals_the_separate_pass(engines):
+    """Tower.fuse_delta: delta = rowsum(dO o O) from the epilogue of the out_proj dgrad GEMM (fp32 accumulator x saved O) instead of
+    attn_delta_kernel on the rounded dO: same prompt gradients up to that rounding, both towers."""
+    vision, text = engines
+    B = 4
+    images, tokens = S.make_images(B, 41).cuda(), S.make_tokens(B, 41).cuda()
+    fac = {k: v.cuda() for k, v in S.make_prompt_factors(7).items()}
+    vis, txt = lpi_step.reconstruct(fac)
+    d = torch.randn(B, 512, generator=torch.Generator().manual_seed(5)).cuda() * 1e-2
+    for eng, inp, table in ((vision, images, vis), (text, tokens, txt)):
+        res = []
+        for fused in (False, True):
+            eng.tower.fuse_delta = fused
+            try:
+                tape = {}
+                eng.forward(inp, table.unsqueeze(0), None, tape, ())
+                res.append(eng.backward(tape, d))
+            finally:
+                eng.tower.fuse_delta = True
+        assert _rel(res[1], res[0]) < 2e-3, (type(eng).__name__, _rel(res[1], res[0]))
