@@ -340,8 +340,8 @@ __global__ void inject_prompt_rows_kernel(float* __restrict__ x, const float* __
 // slice of the projection for them with the D-long reduction split over its 8 warps (partials combined through smem); the L2
 // normalisation over E follows in head_norm_kernel.
 constexpr int HB = 8;
-// KC = projection rows whose loads are in flight together (32 when the per-warp span allows: three L2 round trips per warp at D = 768
-// instead of twelve -- this kernel sits on the serial stretch between the towers' forward and backward)
+// KC = projection rows whose loads are in flight together.  8: with 32 the kernel measured 40-58 us against 15-22 us (ncu, cold caches),
+// so the wider batch is not used
 template <int KC>
 __global__ void __launch_bounds__(256)
 head_fwd_kernel(const float* __restrict__ x, const int* __restrict__ row_idx, const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -754,8 +754,7 @@ extern "C" int lpi_head_fwd(const float* x, const int* row_idx, const float* ln_
     const int smem = (HB * D + 8 * HB * 32) * sizeof(float);
     if (smem > 48 * 1024) return set_error(LPI_ERR_UNSUPPORTED, "head_fwd: D=%d too wide", D);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if ((D / 8) % 32 == 0) head_fwd_kernel<32><<<dim3((B + HB - 1) / HB, (E + 31) / 32), 256, smem, st>>>(x, row_idx, ln_gamma, ln_beta, proj, z_out, B, D, E, eps);
-    else head_fwd_kernel<8><<<dim3((B + HB - 1) / HB, (E + 31) / 32), 256, smem, st>>>(x, row_idx, ln_gamma, ln_beta, proj, z_out, B, D, E, eps);
+    head_fwd_kernel<8><<<dim3((B + HB - 1) / HB, (E + 31) / 32), 256, smem, st>>>(x, row_idx, ln_gamma, ln_beta, proj, z_out, B, D, E, eps);
     head_norm_kernel<<<(B * 32 + 255) / 256, 256, 0, st>>>(z_out, feat_out, B, E);
     return check_launch("head_fwd");
 }
@@ -769,8 +768,7 @@ extern "C" int lpi_head_fwd_select(const float* x, const int* row_idx, const flo
     const int smem = (HB * D + 8 * HB * 32) * sizeof(float);
     if (smem > 48 * 1024) return set_error(LPI_ERR_UNSUPPORTED, "head_fwd_select: D=%d too wide", D);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if ((D / 8) % 32 == 0) head_fwd_kernel<32><<<dim3((B + HB - 1) / HB, (E + 31) / 32), 256, smem, st>>>(x, row_idx, ln_gamma, ln_beta, proj, z_out, B, D, E, eps);
-    else head_fwd_kernel<8><<<dim3((B + HB - 1) / HB, (E + 31) / 32), 256, smem, st>>>(x, row_idx, ln_gamma, ln_beta, proj, z_out, B, D, E, eps);
+    head_fwd_kernel<8><<<dim3((B + HB - 1) / HB, (E + 31) / 32), 256, smem, st>>>(x, row_idx, ln_gamma, ln_beta, proj, z_out, B, D, E, eps);
     head_norm_select_kernel<<<(B * 32 + 255) / 256, 256, 0, st>>>(z_out, feat_out, centers, n_tasks, n_centers, sel_out, B, E);
     return check_launch("head_fwd_select");
 }
