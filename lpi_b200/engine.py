@@ -129,6 +129,10 @@ class Tower:
         # (ops.gemm_do_delta) instead of a separate pass over dO and O per block; LPI_FUSED_DELTA=0 runs the separate kernel
         self.fuse_delta = os.environ.get("LPI_FUSED_DELTA", "1") != "0"
 
+    def rows_only(self, L: int) -> bool:
+        """Does forward(..., out_rows=rows) return [B, D] (last block on the read rows) for sequences of L tokens?"""
+        return self.last_block_rows and not self.tf32 and L <= 512      # the one-row attention kernels are built for L <= 512
+
     # -------------------------------------------------------------------------------------------- forward
     def forward(self, x: torch.Tensor, B: int, L: int, tape: Optional[TowerTape] = None,
                 inject: Optional[dict] = None, out_rows: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -139,7 +143,7 @@ class Tower:
         H = self.heads
         if self.tf32:
             return self._forward_tf32(x, B, L, tape, inject)
-        if not self.last_block_rows:
+        if not self.rows_only(L):
             out_rows = None
         n_blocks = len(self.blocks)
         for li, w in enumerate(self.blocks):
@@ -340,7 +344,7 @@ class VisionEngine:
         ttape = TowerTape(B, L) if tape is not None else None
         rows = torch.arange(B, device=x.device, dtype=torch.int32) * L          # the CLS rows: all the head reads (model.py:254)
         x = self.tower.forward(x, B, L, ttape, inject, out_rows=rows)
-        if self.tower.last_block_rows:
+        if self.tower.rows_only(L):
             rows = torch.arange(B, device=x.device, dtype=torch.int32)          # x is [B, D] already
         task_id = None
         if centers is not None:
@@ -442,7 +446,7 @@ class TextEngine:
         ttape = TowerTape(B, L) if tape is not None else None
         rows = (torch.arange(B, device=x.device, dtype=torch.int64) * L + tokens.argmax(dim=-1)).to(torch.int32)   # EOT row
         x = self.tower.forward(x, B, L, ttape, inject, out_rows=rows)
-        if self.tower.last_block_rows:
+        if self.tower.rows_only(L):
             rows = torch.arange(B, device=x.device, dtype=torch.int32)          # x is [B, D] already
         feat, z = ops.head_fwd(x, rows, self.ln_final[0], self.ln_final[1], self.proj)
         if tape is not None:
@@ -481,7 +485,7 @@ class TextEngine:
         ttape = TowerTape(B, L) if tape is not None else None
         rows = (torch.arange(B, device=x.device, dtype=torch.int64) * L + tokens.argmax(dim=-1)).to(torch.int32)
         x = self.tower.forward(x, B, L, ttape, inject, out_rows=rows)
-        if self.tower.last_block_rows:
+        if self.tower.rows_only(L):
             rows = torch.arange(B, device=x.device, dtype=torch.int32)
         feat, z = ops.head_fwd(x, rows, self.ln_final[0], self.ln_final[1], self.proj)
         if tape is not None:
