@@ -291,3 +291,37 @@ def test_fused_delta_equals_the_separate_pass(engines):
             finally:
                 eng.tower.fuse_delta = True
         assert _rel(res[1], res[0]) < 2e-3, (type(eng).__name__, _rel(res[1], res[0]))
+
+
+_SWITCH_PROBE = """
+import torch, hashlib
+from lpi_b200 import lpi_step, synthetic as S
+from lpi_b200.engine import TextEngine, VisionEngine
+dev = torch.device("cuda")
+sd = S.make_clip_state_dict(0)
+vision, text = VisionEngine(sd, dev), TextEngine(sd, dev)
+fac = {k: v.to(dev) for k, v in S.make_prompt_factors(3).items()}
+r = lpi_step.train_step(vision, text, fac, S.make_images(12, 5).to(dev), S.make_tokens(12, 5).to(dev), 1 / 0.07)      # 12 x 213 rows: the c_fc / dGELU GEMMs have more tiles than CTA pairs
+h = hashlib.sha256()
+for t in [r["img_f"], r["txt_f"], r["losses"]["base_loss"].reshape(1)] + [r["grads"][k] for k in lpi_step.FACTOR_NAMES]:
+    h.update(t.detach().float().cpu().numpy().tobytes())
+print("digest", h.hexdigest())
+"""
+
+
+def test_launch_plumbing_switches_do_not_change_results():
+    """Programmatic dependent launch (LPI_PDL) and the dynamic CLC tile scheduler (LPI_GEMM_CLC) only change WHEN kernels and tiles
+    start, never what they compute: a whole training step (features, loss, all five factor gradients) is bit-identical with PDL off,
+    with CLC on, and by default -- a kernel that touched its inputs before griddepcontrol.wait, or a tile visited twice / never,
+    would show up here.  The switches are read once per process, hence child processes."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    digests = {}
+    for name, env in (("default", {}), ("pdl_off", {"LPI_PDL": "0"}), ("clc_on", {"LPI_GEMM_CLC": "1"})):
+        e = dict(os.environ, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""), **env)
+        r = subprocess.run([sys.executable, "-c", _SWITCH_PROBE], cwd=root, env=e, capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        digests[name] = [l for l in r.stdout.splitlines() if l.startswith("digest")][-1]
+    assert digests["pdl_off"] == digests["default"] and digests["clc_on"] == digests["default"], digests
